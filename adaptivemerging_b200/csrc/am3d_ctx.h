@@ -1,0 +1,187 @@
+// Device-resident state of one am3d context (one GPU, one stream).
+//
+// Layout in HBM (DESIGN.md "Data layout"): every per-body / per-shape / per-contact quantity is a
+// separate flat array (structure of arrays), doubles for all physics, int32 for ids and flags.  Bodies
+// live in a "solver body" index space [0,NB) = leaf bodies in XML parse order, [NB, NB+NCcap) =
+// RigidCollection slots, so that the PGS kernels address a merged collection exactly like a free body.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/am3d.h"
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) throw AmError(AM3D_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+struct AmError {
+  int code;
+  std::string msg;
+  AmError(int c, const std::string& m) : code(c), msg(m) {}
+};
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { T* tp = p; size_t tc = cap; p = o.p; cap = o.cap; o.p = tp; o.cap = tc; }
+    return *this;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+  void ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+    if (n <= cap) return;
+    size_t ncap = n + n / 4 + 64;
+    T* q = nullptr;
+    CK(cudaMalloc(&q, ncap * sizeof(T)));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (p) { CK(cudaStreamSynchronize(st)); cudaFree(p); }
+    p = q;
+    cap = ncap;
+  }
+  void zero(size_t n, cudaStream_t st) { if (n) CK(cudaMemsetAsync(p, 0, n * sizeof(T), st)); }
+  void free_() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  operator T*() const { return p; }
+};
+
+// per-contact arrays (one set for the current step, one for the previous step: warm-start source)
+struct ContactSet {
+  int n = 0;
+  DevBuf<int> b1, b2;        // Contact.body1/body2 (leaf or composite-parent ids)
+  DevBuf<int> s1, s2;        // shapes (part = shape - body_shape_first)
+  DevBuf<int> bv1, bv2, info, leaf;
+  DevBuf<int> bpc;           // index of the body pair this contact belongs to (-1: pinned-pinned)
+  DevBuf<int> state, isNew;
+  DevBuf<unsigned long long> key0;  // (bodyLo<<40 | bodyHi<<16 | partLo<<8 | partHi)
+  DevBuf<unsigned long long> key1;  // (bvLo+2)<<36 | (bvHi+2)<<8 | info      (normalised to lo/hi side)
+  DevBuf<double> pW, nW, t1W, t2W;  // world frame at Contact.set time [3]
+  DevBuf<double> pB1, nB1, t1B1, t2B1;  // same frame in body1 coordinates [3]
+  DevBuf<double> viol, prevViol;
+  DevBuf<double> lam, lamWarm;      // [3]
+  void ensure(size_t c) {
+    b1.ensure(c); b2.ensure(c); s1.ensure(c); s2.ensure(c); bv1.ensure(c); bv2.ensure(c); info.ensure(c); leaf.ensure(c);
+    bpc.ensure(c); state.ensure(c); isNew.ensure(c); key0.ensure(c); key1.ensure(c);
+    pW.ensure(3 * c); nW.ensure(3 * c); t1W.ensure(3 * c); t2W.ensure(3 * c);
+    pB1.ensure(3 * c); nB1.ensure(3 * c); t1B1.ensure(3 * c); t2B1.ensure(3 * c);
+    viol.ensure(c); prevViol.ensure(c); lam.ensure(3 * c); lamWarm.ensure(3 * c);
+  }
+};
+
+// per body-pair arrays (BodyPairContact.java)
+struct BpcSet {
+  int n = 0;
+  DevBuf<unsigned long long> key;  // bodyLo<<32 | bodyHi, ascending
+  DevBuf<int> b1, b2;              // orientation at creation
+  DevBuf<int> start, count;        // contact range in the ContactSet
+  DevBuf<int> nActive;             // contacts with |lambda0| > 1e-14 after the solve
+  DevBuf<double> metricHist;       // [4]
+  DevBuf<int> stateHist;           // [4]
+  DevBuf<int> nMetric, nState;
+  DevBuf<int> alive;
+  void ensure(size_t c) {
+    key.ensure(c); b1.ensure(c); b2.ensure(c); start.ensure(c); count.ensure(c); nActive.ensure(c);
+    metricHist.ensure(4 * c); stateHist.ensure(4 * c); nMetric.ensure(c); nState.ensure(c); alive.ensure(c);
+  }
+};
+
+struct am3d_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string lastError;
+  am3d_params P;
+  bool haveScene = false;
+  int totalSteps = 0;
+  bool mergingEvent = false;
+
+  // ---- host copy of the scene (for reset) -------------------------------------------------
+  struct HostScene {
+    int nb = 0, nsh = 0, nn = 0, nsp = 0, nscenes = 1;
+    std::vector<int> body_type, body_flags, body_scene, body_shape_first, body_shape_count, body_bb_count;
+    std::vector<double> body_x, body_R, body_v, body_omega, body_mass, body_minv, body_mA0, body_jinv0, body_fric,
+        body_rest, body_bbB;
+    std::vector<int> shape_type, shape_body, shape_root;
+    std::vector<double> shape_size, shape_radius, shape_p, shape_lR, shape_lt;
+    std::vector<double> node_c, node_r;
+    std::vector<int> node_first, node_count, node_rank;
+    std::vector<int> sp_type, sp_b1, sp_b2;
+    std::vector<double> sp_pb1, sp_pb2, sp_pw, sp_k, sp_d, sp_l0, sp_ls;
+  } H;
+
+  int NB = 0, NS = 0, NSH = 0, NN = 0, NSP = 0;
+
+  // ---- solver bodies [NS] ---------------------------------------------------------------------
+  DevBuf<double> x, R, v, w, force, torque, dv, minv, mass, jinv, jinv0, mA, mA0, fric, rest, bbB;
+  DevBuf<int> bbCount, flags, scene, parent, btype, collAlive;
+  int nCollections = 0;
+  long long nextStamp = 0;
+  DevBuf<long long> stamp;
+  DevBuf<double> metricHist;  // [10] ring (ordered oldest..newest)
+  DevBuf<int> metricCount, hasExt;
+  DevBuf<int> bShapeFirst, bShapeCount;
+
+  // ---- shapes [NSH] ---------------------------------------------------------------------------
+  DevBuf<int> shType, shBody, shRoot, shLarge;
+  DevBuf<double> shSize, shRadius, shP, shLR, shLt, shX, shR, shBoundC, shBoundR;  // shX/shR: world transform this step
+  // ---- sphere-tree nodes [NN] -------------------------------------------------------------------
+  DevBuf<double> ndC, ndR;
+  DevBuf<int> ndFirst, ndCount, ndRank;
+  // ---- springs ------------------------------------------------------------------------------------
+  DevBuf<int> spType, spB1, spB2;
+  DevBuf<double> spPb1, spPb2, spPw, spK, spD, spL0, spLs;
+  DevBuf<int> spBodyStart, spBodyList;  // CSR body -> (spring<<1 | side), in spring order
+  int nSpringBodies = 0;
+  DevBuf<int> spBodies;
+
+  // ---- broadphase ---------------------------------------------------------------------------------
+  std::vector<int> hSmall, hLarge, hPlanes;
+  DevBuf<int> smallList, largeList, planeList;
+  int nSmall = 0, nLarge = 0, nPlanes = 0;
+  double cellSize = 1.0;
+  DevBuf<unsigned long long> cellKey, cellKeySorted;
+  DevBuf<int> cellVal, cellValSorted;
+  DevBuf<unsigned long long> pairKey, pairKeySorted, pairVal, pairValSorted;
+  DevBuf<int> counters;  // small device scalars
+  DevBuf<unsigned char> cubTemp;
+  int nPairs = 0;
+  DevBuf<int> pairType, pairCap, pairSlot, pairCount, pairOut;
+  // raw hits (slot layout)
+  DevBuf<double> hitPos, hitNrm, hitViol;
+  DevBuf<int> hitMeta;  // [4]: info, bv1, bv2, leaf
+  long long nSlots = 0;
+
+  ContactSet cur, prev;
+  BpcSet bp, bpPrev;
+
+  // ---- solver (colour order) ----------------------------------------------------------------------
+  DevBuf<int> grpColor, grpOrder, grpSb1, grpSb2, grpPos, grpVal, colorHist, tmpI0, tmpI1;
+  DevBuf<unsigned long long> grpKey, grpKeySorted;
+  DevBuf<unsigned long long> grpPrio, bodyBest, bodyMask;
+  DevBuf<int> grpList, grpList2;
+  DevBuf<int> sgB1, sgB2, sgStart, sgCount, sgFlags, sgBpc;  // per solve group (colour-major)
+  DevBuf<double> sgMass;                            // [20] minv1,jinv1,minv2,jinv2
+  DevBuf<double> sgMu;
+  DevBuf<double> scD, scR, scB, scDiag, scLam;      // per contact in solve order: dirs[9], r1r2[6], b[3], D[3], lam[3]
+  DevBuf<int> scSrc;                                // solve-order -> canonical contact index
+  DevBuf<int> scState;
+  std::vector<int> colorStart;                      // host copy, ncolors+1
+  DevBuf<int> dColorStart;
+  int nColors = 0, nGroups = 0;
+  DevBuf<unsigned long long> iterState;             // [0]=max bits, [1]=done, [2]=iters executed
+
+  // ---- timing --------------------------------------------------------------------------------------
+  am3d_timings T;
+  cudaEvent_t ev[16];
+  bool evCreated = false;
+  long long solveLaunches = 0;
+  long long kernelLaunches = 0;
+  double rowUpdates = 0, solveSeconds = 0;
+};

@@ -1,0 +1,886 @@
+// Kernels 3, 4 and 6 of the north star plus the per-step bookkeeping kernels:
+//   external forces (RigidBodySystem.java:234-290, Spring.java:153-209), body-pair bookkeeping
+//   (CollisionProcessor.java:145-226), warm start (:481-665), sleeping (Sleeping.java:49-139),
+//   contact frame / Jacobian / b / D assembly (Contact.java:235-354), graph-coloured projected
+//   Gauss-Seidel (PGS.java:73-256), integration (RigidBody.java:382-441), motion metric
+//   (MotionMetricProcessor.java:39-73, BodyPairContact.java:83-121).
+#pragma once
+#include "am3d_ctx.h"
+#include "am3d_math.cuh"
+
+#define BLK 256
+static inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// forces
+// ------------------------------------------------------------------------------------------------
+// clearBodies :190-202 + RigidCollection.clearBodies :100-105 + applyGravityForce :276-290
+__global__ void k_clear_gravity(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
+                                const double* __restrict__ mass, const double* __restrict__ x, double* __restrict__ v,
+                                double* __restrict__ w, double* __restrict__ force, double* __restrict__ torque,
+                                double* __restrict__ dv, int useGravity, double gx, double gy) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb && !alive[i - nb]) return;
+  if (i < nb && parent[i] >= 0) {
+    // RigidCollection.applyVelocitiesTo :925-937
+    int c = parent[i];
+    d3 r = vsub(ld3(x + 3 * i), ld3(x + 3 * c));
+    d3 om = ld3(w + 3 * c);
+    d3 wxr = vcross(om, r);
+    st3(v + 3 * i, vadd(ld3(v + 3 * c), wxr));
+    st3(w + 3 * i, om);
+  }
+  d3 f(0, 0, 0);
+  if (useGravity) {
+    double m = mass[i];
+    d3 tmp = vscale(-m, d3(gx, gy, 0));
+    f = vadd(f, tmp);
+  }
+  st3(force + 3 * i, f);
+  st3(torque + 3 * i, d3(0, 0, 0));
+#pragma unroll
+  for (int k = 0; k < 6; k++) dv[6 * i + k] = 0.0;
+}
+
+__device__ __forceinline__ d3 spatialVelocity(const double* x, const double* v, const double* w, int b, const d3& pW) {
+  d3 tmp = vsub(pW, ld3(x + 3 * b));
+  d3 r = vcross(ld3(w + 3 * b), tmp);
+  return vadd(r, ld3(v + 3 * b));
+}
+__device__ __forceinline__ void applyForceW(double* force, double* torque, const double* x, int b, const d3& pW, const d3& fW,
+                                            bool atomic) {
+  d3 tmp = vsub(pW, ld3(x + 3 * b));
+  d3 tq = vcross(tmp, fW);
+  if (!atomic) {
+    st3(force + 3 * b, vadd(ld3(force + 3 * b), fW));
+    st3(torque + 3 * b, vadd(ld3(torque + 3 * b), tq));
+  } else {
+    atomicAdd(force + 3 * b, fW.x); atomicAdd(force + 3 * b + 1, fW.y); atomicAdd(force + 3 * b + 2, fW.z);
+    atomicAdd(torque + 3 * b, tq.x); atomicAdd(torque + 3 * b + 1, tq.y); atomicAdd(torque + 3 * b + 2, tq.z);
+  }
+}
+
+// One thread per body that has springs; its (spring, side) entries are visited in spring-list order so
+// the accumulation order into force/torque is the reference's (applySpringForces :309-323).
+__global__ void k_springs(int nsb, const int* __restrict__ spBodies, const int* __restrict__ start,
+                          const int* __restrict__ list, const int* __restrict__ spType, const int* __restrict__ spB1,
+                          const int* __restrict__ spB2, const double* __restrict__ pb1, const double* __restrict__ pb2,
+                          const double* __restrict__ pw, const double* __restrict__ K, const double* __restrict__ D,
+                          const double* __restrict__ L0, const double* __restrict__ LS, double ks, double ds,
+                          const int* __restrict__ parent, const double* __restrict__ x, const double* __restrict__ R,
+                          const double* __restrict__ v, const double* __restrict__ w, double* __restrict__ force,
+                          double* __restrict__ torque) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nsb) return;
+  int body = spBodies[t];
+  for (int e = start[t]; e < start[t + 1]; e++) {
+    int s = list[e] >> 1, side = list[e] & 1;
+    int b1 = spB1[s];
+    xf T1;
+    T1.R = ldm(R + 9 * b1);
+    T1.t = ld3(x + 3 * b1);
+    d3 p1W = xfP(T1, ld3(pb1 + 3 * s));
+    d3 f;
+    d3 at;
+    if (spType[s] == AM3D_SPRING_BODYBODY) {
+      int b2 = spB2[s];
+      xf T2;
+      T2.R = ldm(R + 9 * b2);
+      T2.t = ld3(x + 3 * b2);
+      d3 p2W = xfP(T2, ld3(pb2 + 3 * s));
+      d3 disp = vsub(p2W, p1W);
+      double dist = vlen(disp);
+      if (dist < 1e-3) continue;
+      disp = vscale(1. / dist, disp);
+      d3 v2 = spatialVelocity(x, v, w, b2, p2W);
+      d3 v1 = spatialVelocity(x, v, w, b1, p1W);
+      d3 rel = vsub(v2, v1);
+      double fi = K[s] * ks * (dist - L0[s] * LS[s]) + D[s] * ds * vdot(rel, disp);
+      if (side == 0) { f = vscale(fi, disp); at = p1W; }
+      else { f = vscale(-fi, disp); at = p2W; }
+    } else {
+      d3 disp = vsub(ld3(pw + 3 * s), p1W);
+      double len = vlen(disp);
+      if (len < 1e-3) continue;
+      d3 v1 = spatialVelocity(x, v, w, b1, p1W);
+      double sc = -(K[s] * ks * (len - L0[s] * LS[s]) - D[s] * ds * (vdot(v1, disp) / len)) / len;
+      f = vscale(-sc, disp);
+      at = p1W;
+    }
+    applyForceW(force, torque, x, body, at, f, false);
+    if (parent[body] >= 0) applyForceW(force, torque, x, parent[body], at, f, true);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// body pairs
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bpc_heads(int nc, const unsigned long long* __restrict__ key0, const int* __restrict__ b1,
+                            const int* __restrict__ b2, const int* __restrict__ flags, int* __restrict__ head) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  unsigned long long k = key0[i] >> 16;
+  bool skip = (flags[b1[i]] & AM3D_F_PINNED) && (flags[b2[i]] & AM3D_F_PINNED);  // storeInBodyPairContacts :173
+  int h = 0;
+  if (!skip) {
+    if (i == 0) h = 1;
+    else {
+      unsigned long long kp = key0[i - 1] >> 16;
+      h = (kp != k) ? 1 : 0;
+    }
+  }
+  head[i] = h;
+}
+__global__ void k_bpc_fill(int nc, const unsigned long long* __restrict__ key0, const int* __restrict__ head,
+                           const int* __restrict__ scan, const int* __restrict__ cb1, const int* __restrict__ cb2,
+                           const int* __restrict__ flags, int* __restrict__ cbpc, unsigned long long* __restrict__ bkey,
+                           int* __restrict__ bstart, int* __restrict__ bb1, int* __restrict__ bb2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  bool skip = (flags[cb1[i]] & AM3D_F_PINNED) && (flags[cb2[i]] & AM3D_F_PINNED);
+  int b = scan[i] + head[i] - 1;
+  cbpc[i] = skip ? -1 : b;
+  if (head[i]) {
+    bkey[b] = key0[i] >> 16;
+    bstart[b] = i;
+    bb1[b] = cb1[i];
+    bb2[b] = cb2[i];
+  }
+}
+// count + carry the persistent part (histories, creation orientation) over from last step's table
+__global__ void k_bpc_match(int nb, int nc, const unsigned long long* __restrict__ key, const int* __restrict__ start,
+                            int* __restrict__ count, int* __restrict__ b1, int* __restrict__ b2, int* __restrict__ nActive,
+                            double* __restrict__ mh, int* __restrict__ sh, int* __restrict__ nm, int* __restrict__ nst,
+                            int* __restrict__ alive, int np, const unsigned long long* __restrict__ pkey,
+                            const int* __restrict__ pb1, const int* __restrict__ pb2, const double* __restrict__ pmh,
+                            const int* __restrict__ psh, const int* __restrict__ pnm, const int* __restrict__ pnst) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int end = (b + 1 < nb) ? start[b + 1] : nc;
+  count[b] = end - start[b];
+  nActive[b] = 0;
+  alive[b] = 1;
+  unsigned long long k = key[b];
+  int lo = 0, hi = np;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (pkey[mid] < k) lo = mid + 1; else hi = mid;
+  }
+  if (lo < np && pkey[lo] == k) {
+    b1[b] = pb1[lo];
+    b2[b] = pb2[lo];
+    nm[b] = pnm[lo];
+    nst[b] = pnst[lo];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { mh[4 * b + j] = pmh[4 * lo + j]; sh[4 * b + j] = psh[4 * lo + j]; }
+  } else {
+    nm[b] = 0;
+    nst[b] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { mh[4 * b + j] = 0; sh[4 * b + j] = 0; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warm start: one thread per body pair, contacts of the pair in emission order
+// ------------------------------------------------------------------------------------------------
+struct WarmCtx {
+  // current
+  const int *b1, *b2, *s1, *s2, *leaf;
+  const unsigned long long *key0, *key1;
+  const double* pB1;
+  double *lam, *lamWarm, *prevViol;
+  int* isNew;
+  // previous
+  int np;
+  const unsigned long long *pkey0, *pkey1;
+  const int *pb1, *pleaf;
+  const double *ppB1, *pviol;
+  double* plam;
+  // bodies / shapes
+  const int *btype, *shType;
+  const double *x, *R;
+  const int* ndRank;
+};
+
+// find the previous contact equal to (key0, key1); duplicate keys (box x tree leaf hits, Appendix B):
+// the reference's HashMap keeps the LAST one put, i.e. the last in DFS emission order = largest node rank
+__device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsigned long long k1) {
+  int best = -1, bestRank = -1;
+  for (int j = lo; j < hi; j++) {
+    if (W.pkey1[j] == k1) {
+      int lf = W.pleaf[j];
+      int rk = lf >= 0 ? W.ndRank[lf] : 0;
+      if (best < 0 || rk > bestRank) { best = j; bestRank = rk; }
+    }
+  }
+  return best;
+}
+__device__ __forceinline__ void warmTake(const WarmCtx& W, int i, int j, bool zeroDonor) {
+  W.isNew[i] = 0;
+  for (int k = 0; k < 3; k++) {
+    double l = W.plam[3 * j + k];
+    W.lam[3 * i + k] = l;
+    W.lamWarm[3 * i + k] = l;
+    if (zeroDonor) W.plam[3 * j + k] = 0;
+  }
+  W.prevViol[i] = W.pviol[j];
+}
+__device__ __forceinline__ d3 worldPoint(const double* x, const double* R, int b, const d3& pB) {
+  xf T;
+  T.R = ldm(R + 9 * b);
+  T.t = ld3(x + 3 * b);
+  return xfP(T, pB);
+}
+
+__global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int* __restrict__ bcount,
+                             const int* __restrict__ bb1, const int* __restrict__ bb2, WarmCtx W) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp) return;
+  int s = bstart[b], e = s + bcount[b];
+  int t1 = W.btype[bb1[b]], t2 = W.btype[bb2[b]];
+  bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
+  for (int i = s; i < e; i++) {
+    unsigned long long k0 = W.key0[i], k1 = W.key1[i];
+    // range of previous contacts with the same (bodyLo, bodyHi, partLo, partHi)
+    int lo = 0, hi = W.np;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] < k0) lo = mid + 1; else hi = mid; }
+    int rlo = lo;
+    hi = W.np;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] <= k0) lo = mid + 1; else hi = mid; }
+    int rhi = lo;
+    bool vanillaOnly = !boxy;
+    bool doBox = boxy;
+    if (boxy) {
+      // composite parts that are not boxes (CollisionProcessor.java:497-503)
+      bool nb1 = W.btype[W.b1[i]] == AM3D_BODY_COMPOSITE && W.shType[W.s1[i]] != AM3D_SHAPE_BOX;
+      bool nb2 = W.btype[W.b2[i]] == AM3D_BODY_COMPOSITE && W.shType[W.s2[i]] != AM3D_SHAPE_BOX;
+      if (nb1) { vanillaOnly = true; doBox = false; }
+      else if (nb2) { vanillaOnly = true; doBox = true; }  // vanilla, then falls through into the box-box repair
+    }
+    if (vanillaOnly) {
+      int j = warmLookup(W, rlo, rhi, k1);
+      if (j >= 0) warmTake(W, i, j, false); else W.isNew[i] = 1;
+    }
+    if (!doBox) continue;
+    d3 pNew = worldPoint(W.x, W.R, W.b1[i], ld3(W.pB1 + 3 * i));
+    int myInfo = (int)(k1 & 0xff);
+    unsigned long long kbase = k1 & ~0xffULL;
+    int j = warmLookup(W, rlo, rhi, k1);
+    if (j >= 0) {
+      d3 pOld = worldPoint(W.x, W.R, W.pb1[j], ld3(W.ppB1 + 3 * j));
+      double dist = vdist(pNew, pOld);
+      if (dist > 0.05) {
+        double bestDist = dist;
+        int bestJ = j;
+        for (int info = 0; info < 9; info++) {
+          if (info == myInfo) continue;
+          int jj = warmLookup(W, rlo, rhi, kbase | (unsigned long long)info);
+          if (jj < 0) break;
+          pOld = worldPoint(W.x, W.R, W.pb1[jj], ld3(W.ppB1 + 3 * jj));
+          dist = vdist(pNew, pOld);
+          if (dist < bestDist) { bestDist = dist; bestJ = jj; }
+        }
+        j = bestJ;
+        dist = bestDist;
+      }
+      if (dist < 0.05) warmTake(W, i, j, true); else W.isNew[i] = 1;
+    } else {
+      double bestDist = 1.7976931348623157e308;
+      int bestJ = -1;
+      for (int info = 0; info < 9; info++) {
+        int jj = warmLookup(W, rlo, rhi, kbase | (unsigned long long)info);
+        if (jj < 0) break;
+        d3 pOld = worldPoint(W.x, W.R, W.pb1[jj], ld3(W.ppB1 + 3 * jj));
+        double dist = vdist(pNew, pOld);
+        if (dist < bestDist) { bestDist = dist; bestJ = jj; }
+      }
+      if (bestJ >= 0) {
+        if (bestDist < 0.05) warmTake(W, i, bestJ, true);
+      } else {
+        W.isNew[i] = 1;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sleeping
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wakeBody(int b, int* flags, int* metricCount) {
+  if (flags[b] & AM3D_F_SLEEPING) {
+    atomicAnd(flags + b, ~AM3D_F_SLEEPING);
+    metricCount[b] = 0;
+  }
+}
+// Sleeping.wake :107-139, body-pair part
+__global__ void k_wake_pairs(int nbp, const int* __restrict__ bb1, const int* __restrict__ bb2,
+                             const int* __restrict__ parent, int* __restrict__ flags, int* __restrict__ metricCount) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp) return;
+  int b1 = bb1[b], b2 = bb2[b];
+  if ((flags[b1] & AM3D_F_PINNED) || (flags[b2] & AM3D_F_PINNED)) return;
+  int t1 = parent[b1] >= 0 ? parent[b1] : b1, t2 = parent[b2] >= 0 ? parent[b2] : b2;
+  if ((flags[t1] & AM3D_F_SLEEPING) || (flags[t2] & AM3D_F_SLEEPING)) {
+    wakeBody(b1, flags, metricCount); wakeBody(b2, flags, metricCount);
+    wakeBody(t1, flags, metricCount); wakeBody(t2, flags, metricCount);
+  }
+}
+__global__ void k_wake_springs(int nsp, const int* __restrict__ spType, const int* __restrict__ spB1,
+                               const int* __restrict__ spB2, const int* __restrict__ parent, int* __restrict__ flags,
+                               int* __restrict__ metricCount) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsp) return;
+  if (spType[s] != AM3D_SPRING_BODYBODY) return;
+  int b1 = spB1[s], b2 = spB2[s];
+  int t1 = parent[b1] >= 0 ? parent[b1] : b1, t2 = parent[b2] >= 0 ? parent[b2] : b2;
+  bool s1 = flags[t1] & AM3D_F_SLEEPING, s2 = flags[t2] & AM3D_F_SLEEPING;
+  bool p1 = flags[t1] & AM3D_F_PINNED, p2 = flags[t2] & AM3D_F_PINNED;
+  if (s1 != s2 && !(p1 || p2)) {
+    wakeBody(b1, flags, metricCount); wakeBody(b2, flags, metricCount);
+    wakeBody(t1, flags, metricCount); wakeBody(t2, flags, metricCount);
+  }
+}
+
+__device__ __forceinline__ double bodyMetric(int b, const double* x, const double* R, const double* v, const double* w,
+                                             const double* bbB, const int* bbCount) {
+  double largest = 0;
+  xf T;
+  T.R = ldm(R + 9 * b);
+  T.t = ld3(x + 3 * b);
+  int n = bbCount[b];
+  for (int k = 0; k < n; k++) {
+    d3 pW = xfP(T, ld3(bbB + 24 * b + 3 * k));
+    d3 v1 = spatialVelocity(x, v, w, b, pW);
+    largest = fmax(vlen(v1), largest);
+  }
+  return largest;
+}
+__device__ __forceinline__ double pairMetric(int a, int b, const int* flags, const double* x, const double* R,
+                                             const double* v, const double* w, const double* bbB, const int* bbCount) {
+  if (flags[a] & AM3D_F_PINNED) return bodyMetric(b, x, R, v, w, bbB, bbCount);
+  if (flags[b] & AM3D_F_PINNED) return bodyMetric(a, x, R, v, w, bbB, bbCount);
+  double largest = 0;
+  for (int i = 0; i < 2; i++) {
+    int body = i == 0 ? a : b;
+    xf T;
+    T.R = ldm(R + 9 * body);
+    T.t = ld3(x + 3 * body);
+    int n = bbCount[body];
+    for (int k = 0; k < n; k++) {
+      d3 pW = xfP(T, ld3(bbB + 24 * body + 3 * k));
+      d3 v1 = spatialVelocity(x, v, w, a, pW);
+      d3 v2 = spatialVelocity(x, v, w, b, pW);
+      v1 = vsub(v1, v2);
+      largest = fmax(vlen(v1), largest);
+    }
+  }
+  return largest;
+}
+
+// Sleeping.sleep :49-98 for top-level bodies
+__global__ void k_sleep(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
+                        int* __restrict__ flags, const int* __restrict__ hasExt, double* __restrict__ hist,
+                        int* __restrict__ hcount, const double* __restrict__ x, const double* __restrict__ R,
+                        const double* __restrict__ v, const double* __restrict__ w, const double* __restrict__ bbB,
+                        const int* __restrict__ bbCount, int stepAccum, double threshold) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
+  if (flags[i] & AM3D_F_SLEEPING) return;
+  if (hasExt[i]) return;
+  double m = bodyMetric(i, x, R, v, w, bbB, bbCount);
+  int n = hcount[i];
+  double* h = hist + 10 * i;
+  if (stepAccum > 10) stepAccum = 10;
+  // metricHistory.add(m); if (size > stepAccum) remove(0)   (Sleeping.java:153-158)
+  if (n < 10) h[n++] = m;
+  else { for (int k = 0; k + 1 < 10; k++) h[k] = h[k + 1]; h[9] = m; }
+  if (n > stepAccum) { for (int k = 0; k + 1 < n; k++) h[k] = h[k + 1]; n--; }
+  hcount[i] = n;
+  bool sleep = true;
+  double prev = 1.7976931348623157e308;
+  if (n < stepAccum) {
+    sleep = false;
+  } else {
+    for (int k = 0; k < n; k++) {
+      double mk = h[k];
+      if (mk > prev + 5e-5) { sleep = false; break; }
+      if (mk > threshold) { sleep = false; break; }
+      prev = mk;
+    }
+  }
+  if (sleep) flags[i] |= AM3D_F_SLEEPING;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph colouring of the body-pair groups (Jones-Plassmann with per-body colour masks)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int hash32(unsigned int a) {
+  a = (a ^ 61) ^ (a >> 16);
+  a *= 9;
+  a = a ^ (a >> 4);
+  a *= 0x27d4eb2d;
+  a = a ^ (a >> 15);
+  return a;
+}
+// solver bodies of a group: parent collection unless computeInCollection; -1 for a pinned body
+__global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ parent,
+                           const int* __restrict__ flags, int inCollection, int* __restrict__ sb1, int* __restrict__ sb2,
+                           unsigned long long* __restrict__ prio, int* __restrict__ color) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  int a = gb1[g], b = gb2[g];
+  if (!inCollection) {
+    if (parent[a] >= 0) a = parent[a];
+    if (parent[b] >= 0) b = parent[b];
+  }
+  sb1[g] = (flags[a] & AM3D_F_PINNED) ? -1 - a : a;  // pinned: encoded negative (still addressable as -1-v)
+  sb2[g] = (flags[b] & AM3D_F_PINNED) ? -1 - b : b;
+  prio[g] = ((unsigned long long)hash32((unsigned)g) << 32) | (unsigned)(g + 1);
+  color[g] = -1;
+}
+__global__ void k_color_bid(int ng, const int* __restrict__ sb1, const int* __restrict__ sb2,
+                            const unsigned long long* __restrict__ prio, const int* __restrict__ color,
+                            unsigned long long* __restrict__ best) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng || color[g] != -1) return;
+  unsigned long long p = prio[g];
+  if (sb1[g] >= 0) atomicMax(best + sb1[g], p);
+  if (sb2[g] >= 0) atomicMax(best + sb2[g], p);
+}
+// page = which block of 64 colours is being filled; groups whose bodies have no free colour left in this
+// page are deferred to the next one (color = -2 - page marks "waiting for page+1")
+__global__ void k_color_assign(int ng, int page, const int* __restrict__ sb1, const int* __restrict__ sb2,
+                               const unsigned long long* __restrict__ prio, int* __restrict__ color,
+                               unsigned long long* __restrict__ best, unsigned long long* __restrict__ mask,
+                               int* __restrict__ remaining, int* __restrict__ deferred) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng || color[g] != -1) return;
+  unsigned long long p = prio[g];
+  int a = sb1[g], b = sb2[g];
+  bool win = (a < 0 || best[a] == p) && (b < 0 || best[b] == p);
+  if (!win) { atomicAdd(remaining, 1); return; }
+  unsigned long long m = (a >= 0 ? mask[a] : 0ULL) | (b >= 0 ? mask[b] : 0ULL);
+  if (~m == 0ULL) {
+    color[g] = -2 - page;
+    atomicAdd(deferred, 1);
+  } else {
+    int c = __ffsll((long long)~m) - 1;
+    color[g] = page * 64 + c;
+    if (a >= 0) mask[a] |= 1ULL << c;
+    if (b >= 0) mask[b] |= 1ULL << c;
+  }
+  if (a >= 0) best[a] = 0;
+  if (b >= 0) best[b] = 0;
+}
+__global__ void k_color_next_page(int ng, int page, int* __restrict__ color) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  if (color[g] == -2 - page) color[g] = -1;
+}
+__global__ void k_color_sortkey(int ng, const int* __restrict__ color, unsigned long long* __restrict__ key,
+                                int* __restrict__ val, int* __restrict__ hist) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  key[g] = ((unsigned long long)(unsigned)color[g] << 32) | (unsigned)g;
+  val[g] = g;
+  atomicAdd(hist + color[g], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve-order setup + assembly
+// ------------------------------------------------------------------------------------------------
+struct SolveArrays {
+  int *sgB1, *sgB2, *sgStart, *sgCount, *sgFlags, *sgBpc;
+  double *sgMass, *sgMu;
+  double *scD, *scR, *scB, *scDiag, *scLam;
+  int *scSrc, *scState;
+};
+
+// one thread per group in solve order: gather body data (mass packet, friction, magnet flags)
+__global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos -> group */, const int* __restrict__ sb1,
+                              const int* __restrict__ sb2, const int* __restrict__ gb1, const int* __restrict__ gb2,
+                              const int* __restrict__ gcount, const double* __restrict__ minv,
+                              const double* __restrict__ jinv, const double* __restrict__ fric,
+                              const int* __restrict__ flags, int frictionOverride, double frictionVal, SolveArrays S,
+                              int* __restrict__ grpPos) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  int g = order[p];
+  grpPos[g] = p;
+  int a = sb1[g], b = sb2[g];
+  int ia = a >= 0 ? a : -1 - a, ib = b >= 0 ? b : -1 - b;
+  S.sgB1[p] = a >= 0 ? a : -1;
+  S.sgB2[p] = b >= 0 ? b : -1;
+  S.sgCount[p] = gcount[g];
+  S.sgBpc[p] = g;
+  double* M = S.sgMass + 20 * p;
+  M[0] = minv[ia];
+  for (int k = 0; k < 9; k++) M[1 + k] = jinv[9 * ia + k];
+  M[10] = minv[ib];
+  for (int k = 0; k < 9; k++) M[11 + k] = jinv[9 * ib + k];
+  int l1 = gb1[g], l2 = gb2[g];
+  double mu;
+  if (frictionOverride) mu = frictionVal;
+  else {
+    double f1 = fric[l1], f2 = fric[l2];
+    if (f1 < 0.2 || f2 < 0.2) mu = fmin(f1, f2);
+    else if (f1 > 1. || f2 > 1.) mu = fmax(f1, f2);
+    else mu = (f1 + f2) / 2.;
+  }
+  S.sgMu[p] = mu;
+  int fl1 = flags[l1], fl2 = flags[l2];
+  bool clamp = (!(fl1 & AM3D_F_MAGNETIC) || !(fl1 & AM3D_F_MAGNET_ACTIVE)) && (!(fl2 & AM3D_F_MAGNETIC) || !(fl2 & AM3D_F_MAGNET_ACTIVE));
+  S.sgFlags[p] = clamp ? 1 : 0;
+}
+
+// Contact.computeJacobian :235-271, computeB :279-326, computeJMinvJt :340-354; one thread per contact,
+// output in solve order.  Body state is read through the solver-body index (collection parent unless
+// inCollection).
+__global__ void k_assemble(int nc, const int* __restrict__ cbpc, const int* __restrict__ gstart /* bpc -> first contact */,
+                           const int* __restrict__ grpPos, const int* __restrict__ sgStart, const int* __restrict__ cb1,
+                           const int* __restrict__ cb2, const int* __restrict__ parent, int inCollection,
+                           const double* __restrict__ pW, const double* __restrict__ nW, const double* __restrict__ t1W,
+                           const double* __restrict__ t2W, const double* __restrict__ pB1, const double* __restrict__ nB1,
+                           const double* __restrict__ t1B1, const double* __restrict__ t2B1, const double* __restrict__ viol,
+                           const double* __restrict__ lam, const int* __restrict__ cstate, const double* __restrict__ x,
+                           const double* __restrict__ R, const double* __restrict__ v, const double* __restrict__ w,
+                           const double* __restrict__ force, const double* __restrict__ torque,
+                           const double* __restrict__ minv, const double* __restrict__ jinv, const double* __restrict__ rest,
+                           double dt, double feedback, int restOverride, double restVal, SolveArrays S) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  int g = cbpc[i];
+  if (g < 0) return;
+  int idx = sgStart[grpPos[g]] + (i - gstart[g]);
+  int l1 = cb1[i], l2 = cb2[i];
+  int a = l1, b = l2;
+  bool touchesCollection = parent[l1] >= 0 || parent[l2] >= 0;
+  if (!inCollection) {
+    if (parent[a] >= 0) a = parent[a];
+    if (parent[b] >= 0) b = parent[b];
+  }
+  d3 p, n, t1, t2;
+  if (touchesCollection) {
+    // updateJacobiansThatNeedUpdating :326-334: frame re-expressed from body1 coordinates
+    xf T;
+    T.R = ldm(R + 9 * l1);
+    T.t = ld3(x + 3 * l1);
+    p = xfP(T, ld3(pB1 + 3 * i));
+    n = mtransform(T.R, ld3(nB1 + 3 * i));
+    t1 = mtransform(T.R, ld3(t1B1 + 3 * i));
+    t2 = mtransform(T.R, ld3(t2B1 + 3 * i));
+  } else {
+    p = ld3(pW + 3 * i); n = ld3(nW + 3 * i); t1 = ld3(t1W + 3 * i); t2 = ld3(t2W + 3 * i);
+  }
+  d3 r1 = vsub(p, ld3(x + 3 * a)), r2 = vsub(p, ld3(x + 3 * b));
+  double* D = S.scD + 9 * idx;
+  st3(D, n); st3(D + 3, t1); st3(D + 6, t2);
+  st3(S.scR + 6 * idx, r1); st3(S.scR + 6 * idx + 3, r2);
+  // Jacobian rows
+  d3 dir[3] = {n, t1, t2};
+  d3 jaw[3], jbw[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { jaw[k] = vcross(dir[k], r1); jbw[k] = vcross(r2, dir[k]); }
+  double e = (rest[l1] + rest[l2]) / 2.;
+  if (restOverride) e = restVal;
+  double bb[3] = {0, 0, 0};
+  d3 v1 = ld3(v + 3 * a), w1 = ld3(w + 3 * a), v2 = ld3(v + 3 * b), w2 = ld3(w + 3 * b);
+  m3 J1 = ldm(jinv + 9 * a), J2 = ldm(jinv + 9 * b);
+  double mi1 = minv[a], mi2 = minv[b];
+  {
+    d3 tmp = vscaleAdd(mi1 * dt, ld3(force + 3 * a), v1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bb[k] += vdot(tmp, vscale(-1, dir[k]));
+    tmp = mtransform(J1, ld3(torque + 3 * a));
+    tmp = vscale(dt, tmp);
+    tmp = vadd(tmp, w1);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bb[k] += vdot(tmp, jaw[k]);
+    double bBounce = vdot(v1, vscale(-1, n)) + vdot(w1, jaw[0]);
+    bBounce *= e;
+    bb[0] += bBounce;
+    tmp = vscaleAdd(mi2 * dt, ld3(force + 3 * b), v2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bb[k] += vdot(tmp, dir[k]);
+    tmp = mtransform(J2, ld3(torque + 3 * b));
+    tmp = vscale(dt, tmp);
+    tmp = vadd(tmp, w2);
+#pragma unroll
+    for (int k = 0; k < 3; k++) bb[k] += vdot(tmp, jbw[k]);
+    bBounce = vdot(v2, n) + vdot(w2, jbw[0]);
+    bBounce *= e;
+    bb[0] += bBounce;
+    bb[0] += feedback * viol[i];
+  }
+  S.scB[3 * idx] = bb[0]; S.scB[3 * idx + 1] = bb[1]; S.scB[3 * idx + 2] = bb[2];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    d3 jav = vscale(-1, dir[k]);
+    d3 tmp1 = mtransform(J1, jaw[k]), tmp2 = mtransform(J2, jbw[k]);
+    S.scDiag[3 * idx + k] = mi1 * vdot(jav, jav) + vdot(jaw[k], tmp1) + mi2 * vdot(dir[k], dir[k]) + vdot(jbw[k], tmp2);
+    S.scLam[3 * idx + k] = lam[3 * i + k];
+  }
+  S.scSrc[idx] = i;
+  S.scState[idx] = cstate[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// PGS sweeps: one launch per colour, one thread per body-pair group, the group's contacts in sequence
+// ------------------------------------------------------------------------------------------------
+struct PgsParams {
+  double omega, compliance, tolerance, sliding;
+};
+
+__device__ __forceinline__ double dot6(const d3& jv, const d3& jw, const double* dvp) {
+  return (jv.x * dvp[0] + jv.y * dvp[1] + jv.z * dvp[2]) + (jw.x * dvp[3] + jw.y * dvp[4] + jw.z * dvp[5]);
+}
+__device__ __forceinline__ void applyRow(double* dvp, double minv, const double* J, const d3& jv, const d3& jw, double lambda) {
+  double s = minv * lambda;
+  dvp[0] = s * jv.x + dvp[0];
+  dvp[1] = s * jv.y + dvp[1];
+  dvp[2] = s * jv.z + dvp[2];
+  double tx = J[0] * jw.x + J[1] * jw.y + J[2] * jw.z;
+  double ty = J[3] * jw.x + J[4] * jw.y + J[5] * jw.z;
+  double tz = J[6] * jw.x + J[7] * jw.y + J[8] * jw.z;
+  dvp[3] = lambda * tx + dvp[3];
+  dvp[4] = lambda * ty + dvp[4];
+  dvp[5] = lambda * tz + dvp[5];
+}
+
+// MODE 0: confidentWarmStart (PGS.java:250-256); MODE 1: one Gauss-Seidel sweep (:105-181)
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
+            unsigned long long* __restrict__ iterState) {
+  if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
+  int p = gBegin + blockIdx.x * blockDim.x + threadIdx.x;
+  double localMax = 0;
+  if (p < gEnd) {
+    int a = S.sgB1[p], b = S.sgB2[p];
+    int start = S.sgStart[p], cnt = S.sgCount[p];
+    double M[20];
+    const double* Mp = S.sgMass + 20 * p;
+#pragma unroll
+    for (int k = 0; k < 20; k++) M[k] = Mp[k];
+    double mu = S.sgMu[p];
+    bool clamp = S.sgFlags[p] & 1;
+    double dv1[6], dv2[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { dv1[k] = a >= 0 ? dv[6 * a + k] : 0.0; dv2[k] = b >= 0 ? dv[6 * b + k] : 0.0; }
+    for (int c = 0; c < cnt; c++) {
+      int idx = start + c;
+      const double* Dp = S.scD + 9 * idx;
+      d3 dir[3] = {ld3(Dp), ld3(Dp + 3), ld3(Dp + 6)};
+      d3 r1 = ld3(S.scR + 6 * idx), r2 = ld3(S.scR + 6 * idx + 3);
+      double lam[3] = {S.scLam[3 * idx], S.scLam[3 * idx + 1], S.scLam[3 * idx + 2]};
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+          if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, lam[k]);
+          if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, lam[k]);
+        }
+      } else {
+        double bb[3] = {S.scB[3 * idx], S.scB[3 * idx + 1], S.scB[3 * idx + 2]};
+        double DD[3] = {S.scDiag[3 * idx], S.scDiag[3 * idx + 1], S.scDiag[3 * idx + 2]};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+          double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
+          double prev = lam[k];
+          double l = (DD[k] * prev - P.omega * (bb[k] + Jdv)) / (DD[k] + P.compliance);
+          if (clamp) {
+            if (k == 0) l = fmax(0.0, l);
+            else {
+              double limit = mu * lam[0];
+              l = fmax(l, -limit);
+              l = fmin(l, limit);
+            }
+          }
+          lam[k] = l;
+          double diff = l - prev;
+          if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
+          if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
+          localMax = fmax(localMax, fabs(diff));
+        }
+        S.scLam[3 * idx] = lam[0]; S.scLam[3 * idx + 1] = lam[1]; S.scLam[3 * idx + 2] = lam[2];
+        if (lastIter) {
+          // Contact.updateContactState :385-398
+          d3 jaw1 = vcross(dir[1], r1), jbw1 = vcross(r2, dir[1]);
+          d3 jaw2 = vcross(dir[2], r1), jbw2 = vcross(r2, dir[2]);
+          double w1 = bb[1] + (dot6(vscale(-1, dir[1]), jaw1, dv1) + dot6(dir[1], jbw1, dv2));
+          double w2 = bb[2] + (dot6(vscale(-1, dir[2]), jaw2, dv1) + dot6(dir[2], jbw2, dv2));
+          int st;
+          if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
+          else if (fabs(w1) > P.sliding) st = AM3D_CS_ONEDGE;
+          else if (fabs(w2) > P.sliding) st = AM3D_CS_ONEDGE;
+          else st = AM3D_CS_CLEAR;
+          S.scState[idx] = st;
+        }
+      }
+    }
+    if (a >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+    }
+    if (b >= 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+    }
+  }
+  if (MODE == 1) {
+    // max |delta lambda| of the sweep (PGS.java:125,159,176): non-negative doubles order like their bit patterns
+    for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+    if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
+  }
+}
+__global__ void k_iter_end(unsigned long long* iterState, double tolerance, int checkTolerance) {
+  if (iterState[1]) return;
+  iterState[2] += 1;
+  double m = __longlong_as_double((long long)iterState[0]);
+  if (checkTolerance && m < tolerance) iterState[1] = 1;
+  iterState[3] = iterState[0];
+  iterState[0] = 0;
+}
+
+// copy the solution back to canonical contact order and count active contacts per body pair
+__global__ void k_post_solve(int nc, SolveArrays S, const int* __restrict__ cbpc, double* __restrict__ lam,
+                             int* __restrict__ cstate, int* __restrict__ nActive) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nc) return;
+  int i = S.scSrc[idx];
+  double l0 = S.scLam[3 * idx];
+  lam[3 * i] = l0; lam[3 * i + 1] = S.scLam[3 * idx + 1]; lam[3 * i + 2] = S.scLam[3 * idx + 2];
+  cstate[i] = S.scState[idx];
+  if (nActive && cbpc[i] >= 0 && fabs(l0) > 1e-14) atomicAdd(nActive + cbpc[i], 1);  // clearBodyPairContacts :213-226
+}
+
+// ------------------------------------------------------------------------------------------------
+// integration
+// ------------------------------------------------------------------------------------------------
+// RigidBody.advanceVelocities :409-417 for awake, unpinned top-level bodies
+__global__ void k_advance_velocities(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
+                                     const int* __restrict__ flags, const double* __restrict__ minv,
+                                     const double* __restrict__ jinv, const double* __restrict__ force,
+                                     const double* __restrict__ torque, const double* __restrict__ dv,
+                                     double* __restrict__ v, double* __restrict__ w, double dt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
+  if (flags[i] & (AM3D_F_PINNED | AM3D_F_SLEEPING)) return;
+  d3 vv = vscaleAdd(dt * minv[i], ld3(force + 3 * i), ld3(v + 3 * i));
+  vv = vadd(vv, ld3(dv + 6 * i));
+  d3 dom = mtransform(ldm(jinv + 9 * i), ld3(torque + 3 * i));
+  dom = vscale(dt, dom);
+  d3 ww = vadd(ld3(w + 3 * i), dom);
+  ww = vadd(ww, ld3(dv + 6 * i + 3));
+  st3(v + 3 * i, vv);
+  st3(w + 3 * i, ww);
+}
+
+// RigidBody.advancePositions :427-441 (expRodrigues :382-401) + viscous decay (RigidBodySystem.java:428-436)
+__global__ void k_advance_positions(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
+                                    const int* __restrict__ flags, double* __restrict__ x, double* __restrict__ R,
+                                    const double* __restrict__ v, const double* __restrict__ w,
+                                    const double* __restrict__ jinv0, const double* __restrict__ mA0,
+                                    double* __restrict__ jinv, double* __restrict__ mA, double dt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
+  if (flags[i] & (AM3D_F_PINNED | AM3D_F_SLEEPING)) return;
+  d3 vv = ld3(v + 3 * i), om = ld3(w + 3 * i);
+  st3(x + 3 * i, vscaleAdd(dt, vv, ld3(x + 3 * i)));
+  double t = vlen(om) * dt;
+  m3 Rm = ldm(R + 9 * i);
+  if (t > 1e-8) {
+    d3 wn = vnormalize(om);
+    double c = cos(t), s = sin(t);
+    double c1 = 1 - c;
+    m3 dR;
+    dR.m[0] = c + wn.x * wn.x * c1;
+    dR.m[3] = wn.z * s + wn.x * wn.y * c1;
+    dR.m[6] = -wn.y * s + wn.x * wn.z * c1;
+    dR.m[1] = -wn.z * s + wn.x * wn.y * c1;
+    dR.m[4] = c + wn.y * wn.y * c1;
+    dR.m[7] = wn.x * s + wn.y * wn.z * c1;
+    dR.m[2] = wn.y * s + wn.x * wn.z * c1;
+    dR.m[5] = -wn.x * s + wn.y * wn.z * c1;
+    dR.m[8] = c + wn.z * wn.z * c1;
+    dR = mmul(dR, Rm);
+    Rm = mnormalizeCP(dR);
+    stm(R + 9 * i, Rm);
+  }
+  stm(mA + 9 * i, rm0rt(Rm, ldm(mA0 + 9 * i)));
+  stm(jinv + 9 * i, rm0rt(Rm, ldm(jinv0 + 9 * i)));
+}
+__global__ void k_viscous(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
+                          double* __restrict__ v, double* __restrict__ w, double a1, double a2) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
+  st3(v + 3 * i, vscale(a1, ld3(v + 3 * i)));
+  st3(w + 3 * i, vscale(a2, ld3(w + 3 * i)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulateForMerging (BodyPairContact.java:83-121) + external-contact flags for Sleeping.sleep
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bpc_accumulate(int nbp, const int* __restrict__ bb1, const int* __restrict__ bb2,
+                                 const int* __restrict__ bstart, const int* __restrict__ bcount,
+                                 const int* __restrict__ nActive, int* __restrict__ alive, const double* __restrict__ lam,
+                                 const int* __restrict__ cstate, const int* __restrict__ parent,
+                                 const int* __restrict__ flags, const double* __restrict__ x, const double* __restrict__ R,
+                                 const double* __restrict__ v, const double* __restrict__ w, const double* __restrict__ bbB,
+                                 const int* __restrict__ bbCount, double* __restrict__ mh, int* __restrict__ sh,
+                                 int* __restrict__ nm, int* __restrict__ nst, int accum, int* __restrict__ hasExt) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp) return;
+  if (nActive[b] == 0) { alive[b] = 0; return; }  // removeEmptyBodyPairContacts :191-208
+  int l1 = bb1[b], l2 = bb2[b];
+  int a = parent[l1] >= 0 ? parent[l1] : l1, c = parent[l2] >= 0 ? parent[l2] : l2;
+  if (!((flags[l1] & AM3D_F_PINNED) || (flags[l2] & AM3D_F_PINNED))) {
+    hasExt[l1] = 1; hasExt[l2] = 1; hasExt[a] = 1; hasExt[c] = 1;
+  }
+  if (accum > 4) accum = 4;
+  double m = pairMetric(a, c, flags, x, R, v, w, bbB, bbCount);
+  int n = nm[b];
+  if (n < 4) mh[4 * b + n++] = m;
+  else { for (int k = 0; k < 3; k++) mh[4 * b + k] = mh[4 * b + k + 1]; mh[4 * b + 3] = m; }
+  if (n > accum) { for (int k = 0; k + 1 < n; k++) mh[4 * b + k] = mh[4 * b + k + 1]; n--; }
+  nm[b] = n;
+  int notOnEdge = 0, act = 0;
+  for (int i = bstart[b]; i < bstart[b] + bcount[b]; i++) {
+    if (fabs(lam[3 * i]) > 1e-14) {
+      act++;
+      if (cstate[i] != AM3D_CS_ONEDGE) notOnEdge++;
+    }
+  }
+  int st;
+  if (notOnEdge == 0) st = AM3D_CS_ONEDGE;
+  else if (notOnEdge >= 2) st = AM3D_CS_CLEAR;
+  else if (act == 1) st = AM3D_CS_CLEAR;
+  else st = AM3D_CS_ONEDGE;
+  n = nst[b];
+  if (n < 4) sh[4 * b + n++] = st;
+  else { for (int k = 0; k < 3; k++) sh[4 * b + k] = sh[4 * b + k + 1]; sh[4 * b + 3] = st; }
+  if (n > accum) { for (int k = 0; k + 1 < n; k++) sh[4 * b + k] = sh[4 * b + k + 1]; n--; }
+  nst[b] = n;
+}
+
+// stable compaction of the surviving body pairs into next step's "previous" table
+__global__ void k_bpc_compact(int nbp, const int* __restrict__ alive, const int* __restrict__ scan,
+                              const unsigned long long* __restrict__ key, const int* __restrict__ b1,
+                              const int* __restrict__ b2, const double* __restrict__ mh, const int* __restrict__ sh,
+                              const int* __restrict__ nm, const int* __restrict__ nst, unsigned long long* __restrict__ okey,
+                              int* __restrict__ ob1, int* __restrict__ ob2, double* __restrict__ omh, int* __restrict__ osh,
+                              int* __restrict__ onm, int* __restrict__ onst) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp || !alive[b]) return;
+  int o = scan[b];
+  okey[o] = key[b]; ob1[o] = b1[b]; ob2[o] = b2[b]; onm[o] = nm[b]; onst[o] = nst[b];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { omh[4 * o + k] = mh[4 * b + k]; osh[4 * o + k] = sh[4 * b + k]; }
+}

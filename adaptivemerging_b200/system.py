@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's ``RigidBodySystem`` for the hot path.
+
+Same names, argument meaning and error behaviour as ``mergingBodies3D.RigidBodySystem``
+(RigidBodySystem.java:25-66, 102-185, 390-446): ``advanceTime(dt)``, ``reset()``, ``clear()``,
+``jiggle()`` and the timing fields the overlay / CSV read (``computeTime``, ``mergingTime``,
+``unmergingTime``, ``warmStartTime``, ``totalSteps``; ``collision.collisionDetectTime`` ... are exposed
+through ``timings()``).  The reference is Java; with no JVM in this environment the host side above the
+C ABI is written in Python and calls the CUDA library through ctypes exactly as the Java shim in
+INTEGRATION.md would through Panama FFM.  All physics runs on the GPU; this class holds no state beyond
+the opaque context handle.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .ctypes_defs import (BPC_DTYPE, CONTACT_DTYPE, am3d_params, am3d_timings, apply_overrides, default_params)
+from .scene import SceneBlob, load_xml
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RigidBodySystem:
+    def __init__(self, device=0):
+        self._L = _capi.load()
+        h = C.c_void_p()
+        rc = self._L.am3d_create(int(device), C.byref(h))
+        if rc != 0:
+            raise _capi.Am3dError(rc, "am3d_create failed (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.params = default_params()
+        self.blob = None
+        self.name = ""
+        self.simulationTime = 0.0
+        self.totalSteps = 0
+        self.computeTime = 0.0
+        self.totalAccumulatedComputeTime = 0.0
+        self.mergingTime = 0.0
+        self.unmergingTime = 0.0
+        self.warmStartTime = 0.0
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._L.am3d_last_error(self._h)
+            raise _capi.Am3dError(rc, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.am3d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- scene hand-over (what XMLParser.parse leaves in the system) ---------------------------------
+    def load(self, blob: SceneBlob, params: am3d_params = None):
+        self.blob = blob
+        self._scene = blob.as_ctypes()
+        self.params = params if params is not None else apply_overrides(default_params(), blob.overrides)
+        self._ck(self._L.am3d_set_params(self._h, C.byref(self.params)))
+        self._ck(self._L.am3d_upload_scene(self._h, C.byref(self._scene)))
+        self.simulationTime = 0.0
+        self.totalSteps = 0
+        return self
+
+    def loadXML(self, path, copies=1):
+        return self.load(load_xml(path, copies=copies))
+
+    def set_params(self, params: am3d_params):
+        self._ck(self._L.am3d_set_params(self._h, C.byref(params)))
+        self.params = params
+
+    # -- RigidBodySystem API -----------------------------------------------------------------------
+    def advanceTime(self, dt, nsteps=1):
+        self._ck(self._L.am3d_step(self._h, float(dt), int(nsteps)))
+        t = self.timings()
+        self.totalSteps += nsteps
+        self.simulationTime += dt * nsteps
+        self.computeTime = t.compute_time
+        self.totalAccumulatedComputeTime += t.compute_time
+        self.mergingTime = t.merging
+        self.unmergingTime = t.unmerging
+        self.warmStartTime = t.warmstart
+
+    def reset(self):
+        self._ck(self._L.am3d_reset(self._h))
+        self.simulationTime = 0.0
+        self.totalAccumulatedComputeTime = 0.0
+        self.totalSteps = 0
+
+    def clear(self):
+        """RigidBodySystem.clear (:441-446): drop the scene."""
+        self.close()
+        self.__init__(self.device)
+
+    def jiggle(self, seed=None):
+        """RigidBodySystem.jiggle (:85-96): random velocity kick on every unpinned body."""
+        rng = np.random.default_rng(seed)
+        b = self.bodies()
+        pinned = (self.blob.a["body_flags"] & 1) != 0
+        kick_w = rng.random((self.n_bodies, 3)) * 2 - 1
+        kick_v = rng.random((self.n_bodies, 3)) * 2 - 1
+        kick_w[pinned] = 0
+        kick_v[pinned] = 0
+        self.upload_bodies(b["x"], b["R"], b["v"] + kick_v, b["omega"] + kick_w)
+
+    # -- outbound reads ----------------------------------------------------------------------------
+    @property
+    def n_bodies(self):
+        return self._L.am3d_num_bodies(self._h)
+
+    def bodies(self):
+        n = self.n_bodies
+        x = np.empty((n, 3)); R = np.empty((n, 9)); v = np.empty((n, 3)); w = np.empty((n, 3))
+        sl = np.empty(n, np.int32); co = np.empty(n, np.int32)
+        self._ck(self._L.am3d_download_bodies(self._h, _p(x), _p(R), _p(v), _p(w), _p(sl), _p(co)))
+        return dict(x=x, R=R, v=v, omega=w, sleeping=sl, collection=co)
+
+    def upload_bodies(self, x, R, v, omega):
+        x, R, v, omega = [np.ascontiguousarray(a, np.float64) for a in (x, R, v, omega)]
+        self._ck(self._L.am3d_upload_bodies(self._h, _p(x), _p(R), _p(v), _p(omega)))
+
+    def set_body_velocity(self, body, v=None, omega=None):
+        v = np.ascontiguousarray(v, np.float64) if v is not None else None
+        w = np.ascontiguousarray(omega, np.float64) if omega is not None else None
+        self._ck(self._L.am3d_set_body_velocity(self._h, int(body), _p(v), _p(w)))
+
+    def add_body_velocity(self, body, dv=None, domega=None):
+        v = np.ascontiguousarray(dv, np.float64) if dv is not None else None
+        w = np.ascontiguousarray(domega, np.float64) if domega is not None else None
+        self._ck(self._L.am3d_add_body_velocity(self._h, int(body), _p(v), _p(w)))
+
+    def contacts(self, include_internal=False):
+        n = self._L.am3d_num_contacts(self._h, int(include_internal))
+        out = np.zeros(max(n, 1), CONTACT_DTYPE)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_contacts(self._h, _p(out), n, int(include_internal), C.byref(cnt)))
+        return out[:cnt.value]
+
+    def bpcs(self):
+        n = self._L.am3d_num_bpcs(self._h)
+        out = np.zeros(max(n, 1), BPC_DTYPE)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_bpcs(self._h, _p(out), n, C.byref(cnt)))
+        return out[:cnt.value]
+
+    def timings(self) -> am3d_timings:
+        t = am3d_timings()
+        self._ck(self._L.am3d_get_timings(self._h, C.byref(t)))
+        return t
+
+    def stats(self):
+        out = np.zeros(4)
+        self._ck(self._L.am3d_stats(self._h, _p(out)))
+        return dict(kernel_launches=int(out[0]), solve_launches=int(out[1]), row_updates=out[2], solve_seconds=out[3])
+
+    # -- phase-level entry points (parity tests, roofline leg of bench.py) ------------------------------
+    def detect(self):
+        self._ck(self._L.am3d_detect(self._h))
+        return self._L.am3d_num_contacts(self._h, 0)
+
+    def set_lambdas(self, lam):
+        lam = np.ascontiguousarray(lam, np.float64)
+        self._ck(self._L.am3d_set_lambdas(self._h, _p(lam), int(lam.size // 3)))
+
+    def solve(self, dt=0.05):
+        self._ck(self._L.am3d_solve(self._h, float(dt)))
+
+    def deltav(self):
+        dv = np.empty((self.n_bodies, 6))
+        self._ck(self._L.am3d_download_deltav(self._h, _p(dv)))
+        return dv
+
+    def solve_order(self):
+        n = self._L.am3d_num_contacts(self._h, 0)
+        out = np.zeros(max(n, 1), np.int32)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_solve_order(self._h, _p(out), n, C.byref(cnt)))
+        return out[:cnt.value]

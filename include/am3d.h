@@ -304,6 +304,10 @@ int am3d_upload_contacts(am3d_ctx* ctx, const am3d_contact* in, int count);
  * current contacts; fills lambda, deltaV and contact states */
 int am3d_solve(am3d_ctx* ctx, double dt);
 int am3d_download_deltav(am3d_ctx* ctx, double* dv /* [n_bodies*6] */);
+/* overwrite the multipliers of the current external contacts (canonical order) before am3d_solve */
+int am3d_set_lambdas(am3d_ctx* ctx, const double* lambda /* [count*3] */, int count);
+/* counters: [0] kernels launched so far, [1] PGS sweep launches, [2] contact-row updates, [3] PGS kernel seconds */
+int am3d_stats(am3d_ctx* ctx, double* out4);
 /* order (position in the Gauss-Seidel sequence) the full solve gave each
  * current external contact, for replaying on the CPU oracle */
 int am3d_download_solve_order(am3d_ctx* ctx, int32_t* order, int capacity, int* count);

@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+from adaptivemerging_b200.ctypes_defs import contact_keys, default_params
+from adaptivemerging_b200.scene import SceneBuilder, box_stack
+
+
+def params(**kw):
+    p = default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def key_index(arr):
+    """dict full-key tuple -> list of indices (box x tree leaf hits share the warm-start key, the leaf
+    field makes the full key unique)."""
+    d = {}
+    for i, k in enumerate(map(tuple, contact_keys(arr).tolist())):
+        d.setdefault(k, []).append(i)
+    return d
+
+
+def assert_contact_sets_equal(cg, co, exact=True, tol=0.0):
+    """Bit-exact comparison of two contact sets (GPU canonical order vs oracle emission order)."""
+    kg, ko = key_index(cg), key_index(co)
+    assert set(kg) == set(ko), (f"contact keys differ: only gpu {sorted(set(kg) - set(ko))[:5]} "
+                                f"only oracle {sorted(set(ko) - set(kg))[:5]} ({len(cg)} vs {len(co)})")
+    ig = np.array([kg[k][0] for k in kg])
+    io = np.array([ko[k][0] for k in kg])
+    assert all(len(v) == 1 for v in kg.values()) and all(len(v) == 1 for v in ko.values())
+    for f in ("point_w", "normal_w", "violation"):
+        a, b = cg[f][ig], co[f][io]
+        if exact:
+            assert np.array_equal(a, b), f"{f} differs: max |d| = {np.abs(a - b).max():.3e}"
+        else:
+            assert np.abs(a - b).max() <= tol, f"{f} differs: {np.abs(a - b).max():.3e}"
+    return ig, io
+
+
+def small_pile(nx=3, ny=4, nz=3):
+    return box_stack(nx, ny, nz, pile=True)
+
+
+def mixed_scene():
+    """boxes, spheres, a plane, a pinned box and a spring-free composite-less mix for detection tests."""
+    sb = SceneBuilder()
+    sb.add_plane((0, 0, 0), (0, 1, 0))
+    sb.add_box((6, 1, 6), (0, 0.5, 0), pinned=True, name="slab")
+    k = 0
+    for i in range(3):
+        for j in range(3):
+            y = 1.6 + 1.05 * ((i + j) % 3)
+            if (i + j) % 2 == 0:
+                sb.add_box((1, 1, 1), (-1.2 + 1.2 * i, y, -1.2 + 1.2 * j), axis_angle=(0, 1, 0, 0.3 * k), name=f"b{k}")
+            else:
+                sb.add_sphere(0.5, (-1.2 + 1.2 * i, y, -1.2 + 1.2 * j), name=f"s{k}")
+            k += 1
+    sb.add_sphere(0.6, (0.1, 3.9, 0.1), v=(0, -1, 0), name="top")
+    return sb.build()
