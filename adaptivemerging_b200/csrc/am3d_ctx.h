@@ -56,6 +56,7 @@ struct DevBuf {
 // per-contact arrays (one set for the current step, one for the previous step: warm-start source)
 struct ContactSet {
   int n = 0;
+  int nSorted = 0;  // entries [0,nSorted) are in canonical key order; the rest was appended by an unmerge
   DevBuf<int> b1, b2;        // Contact.body1/body2 (leaf or composite-parent ids)
   DevBuf<int> s1, s2;        // shapes (part = shape - body_shape_first)
   DevBuf<int> bv1, bv2, info, leaf;
@@ -74,6 +75,16 @@ struct ContactSet {
     pB1.ensure(3 * c); nB1.ensure(3 * c); t1B1.ensure(3 * c); t2B1.ensure(3 * c);
     viol.ensure(c); prevViol.ensure(c); lam.ensure(3 * c); lamWarm.ensure(3 * c);
   }
+  // grow while keeping the existing entries
+  void ensureKeep(size_t c, size_t, cudaStream_t st) {
+    if (c > b1.cap) c = c + c / 2;  // amortise; every field is checked on its own (capacities are not proportional)
+    b1.ensure(c, true, st); b2.ensure(c, true, st); s1.ensure(c, true, st); s2.ensure(c, true, st); bv1.ensure(c, true, st);
+    bv2.ensure(c, true, st); info.ensure(c, true, st); leaf.ensure(c, true, st); bpc.ensure(c, true, st); state.ensure(c, true, st);
+    isNew.ensure(c, true, st); key0.ensure(c, true, st); key1.ensure(c, true, st);
+    pW.ensure(3 * c, true, st); nW.ensure(3 * c, true, st); t1W.ensure(3 * c, true, st); t2W.ensure(3 * c, true, st);
+    pB1.ensure(3 * c, true, st); nB1.ensure(3 * c, true, st); t1B1.ensure(3 * c, true, st); t2B1.ensure(3 * c, true, st);
+    viol.ensure(c, true, st); prevViol.ensure(c, true, st); lam.ensure(3 * c, true, st); lamWarm.ensure(3 * c, true, st);
+  }
 };
 
 // per body-pair arrays (BodyPairContact.java)
@@ -90,6 +101,12 @@ struct BpcSet {
   void ensure(size_t c) {
     key.ensure(c); b1.ensure(c); b2.ensure(c); start.ensure(c); count.ensure(c); nActive.ensure(c);
     metricHist.ensure(4 * c); stateHist.ensure(4 * c); nMetric.ensure(c); nState.ensure(c); alive.ensure(c);
+  }
+  void ensureKeep(size_t c, size_t, cudaStream_t st) {
+    if (c > key.cap) c = c + c / 2;
+    key.ensure(c, true, st); b1.ensure(c, true, st); b2.ensure(c, true, st); start.ensure(c, true, st); count.ensure(c, true, st);
+    nActive.ensure(c, true, st); metricHist.ensure(4 * c, true, st); stateHist.ensure(4 * c, true, st); nMetric.ensure(c, true, st);
+    nState.ensure(c, true, st); alive.ensure(c, true, st);
   }
 };
 
@@ -159,7 +176,25 @@ struct am3d_ctx {
   long long nSlots = 0;
 
   ContactSet cur, prev;
-  BpcSet bp, bpPrev;
+  BpcSet bp, bpPrev, bpTmp;
+  bool bpTail = false;  // bp holds pairs appended by an unmerge (not in key order)
+
+  // ---- merging ------------------------------------------------------------------------------------
+  ContactSet icon, icon2;   // internal contacts of collections (RigidCollection.internalContacts), grouped by pair
+  BpcSet ibp, ibp2;         // internal body pairs (BodyPairContact.inCollection == true)
+  DevBuf<int> ibpCut, ibpCut2;
+  DevBuf<double> B2CR, B2Ct;  // RigidBody.transformB2C of the leaves
+  DevBuf<int> collCount, collStart, members, memVal, changedList, collMode, collFlagAcc, freeList;
+  DevBuf<unsigned int> memKey, memKeySorted;
+  DevBuf<int> uf, mflag, compEnt, needNew, newScan, target, collCuts, collNComp, collKeeps, leavesFlag, leavesScan, freedFlag;
+  DevBuf<unsigned long long> compBest;
+  DevBuf<int> swB1, swB2, swCount, swStart, tmpI2, tmpI3;
+  std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples
+  bool recordOrders = false;
+  std::vector<int> orderFull, orderSweep;
+  std::vector<am3d_contact> orderFullKeys, orderSweepKeys;
+  bool lastSolveSweep = false;
+  int lastSolveN = 0;
 
   // ---- solver (colour order) ----------------------------------------------------------------------
   DevBuf<int> grpColor, grpOrder, grpSb1, grpSb2, grpPos, grpVal, colorHist, tmpI0, tmpI1;

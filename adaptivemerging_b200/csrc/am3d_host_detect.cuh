@@ -1,0 +1,114 @@
+// Host orchestration of detection, body-pair bookkeeping and warm start.
+#pragma once
+#include "am3d_host_util.cuh"
+#include "am3d_detect.cuh"
+#include "am3d_step.cuh"
+static void detect(am3d_ctx* c) {
+  int nsh = c->NSH;
+  std::swap(c->cur, c->prev);  // ContactPool.swapPools (ContactPool.java:60-65): last step's contacts stay readable
+  LAUNCH(c, k_shape_update, nblk(nsh), BLK, nsh, c->shType.p, c->shBody.p, c->shRoot.p, c->shRadius.p, c->shLR.p, c->shLt.p,
+         c->btype.p, c->x.p, c->R.p, c->ndC.p, c->ndR.p, c->shX.p, c->shR.p, c->shBoundC.p, c->shBoundR.p);
+  double inv = 1.0 / c->cellSize;
+  if (c->pairKey.cap == 0) {
+    size_t cap = (size_t)nsh * 8 + 1024;
+    c->pairKey.ensure(cap); c->pairVal.ensure(cap); c->pairKeySorted.ensure(cap); c->pairValSorted.ensure(cap);
+  }
+  if (c->nSmall > 0) {
+    LAUNCH(c, k_cell_keys, nblk(c->nSmall), BLK, c->nSmall, c->smallList.p, c->shBody.p, c->scene.p, c->shBoundC.p, inv,
+           c->cellKey.p, c->cellVal.p);
+    int endBit = std::min(64, 42 + bitsFor((unsigned long long)c->H.nscenes));
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->cellKey.p, c->cellKeySorted.p, c->cellVal.p, c->cellValSorted.p, c->nSmall, 0, endBit, c->stream);
+    });
+  }
+  int np = 0;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CK(cudaMemsetAsync(c->counters.p, 0, sizeof(int), c->stream));
+    PairCtx PC{c->shBody.p, c->bShapeFirst.p, c->parent.p, c->flags.p, c->scene.p, c->stamp.p, c->shBoundC.p, c->shBoundR.p,
+               c->pairKey.p, c->pairVal.p, c->counters.p, (int)std::min<size_t>(c->pairKey.cap, 0x7fffffff)};
+    if (c->nSmall > 0)
+      LAUNCH(c, k_pairs_grid, nblk(c->nSmall), BLK, c->nSmall, c->cellKeySorted.p, c->cellValSorted.p, inv, PC);
+    if (c->nLarge > 0 || c->nPlanes > 0)
+      LAUNCH(c, k_pairs_special, nblk(nsh), BLK, nsh, c->shType.p, c->shLarge.p, c->nLarge, c->largeList.p, c->nPlanes,
+             c->planeList.p, c->shSize.p, c->shRadius.p, PC);
+    np = readInt(c, c->counters.p);
+    if ((size_t)np <= c->pairKey.cap) break;
+    size_t cap = (size_t)np + np / 4 + 1024;
+    c->pairKey.ensure(cap); c->pairVal.ensure(cap); c->pairKeySorted.ensure(cap); c->pairValSorted.ensure(cap);
+  }
+  c->nPairs = np;
+  c->T.n_pairs = np;
+  int nc = 0;
+  if (np > 0) {
+    int endBit = std::min(64, 40 + bitsFor((unsigned long long)c->NB));
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->pairKey.p, c->pairKeySorted.p, c->pairVal.p, c->pairValSorted.p, np, 0, endBit, c->stream);
+    });
+    c->pairType.ensure(np + 1); c->pairCap.ensure(np + 1); c->pairSlot.ensure(np + 1); c->pairCount.ensure(np + 1); c->pairOut.ensure(np + 1);
+    LAUNCH(c, k_pair_classify, nblk(np), BLK, np, c->pairValSorted.p, c->shType.p, c->pairType.p, c->pairCap.p);
+    TreeCtx TC{c->shType.p, c->shRoot.p, c->shSize.p, c->shRadius.p, c->shP.p, c->shX.p, c->shR.p, c->ndC.p, c->ndR.p, c->ndFirst.p, c->ndCount.p};
+    HitOut HO{c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p};
+    bool haveTrees = c->NN > 0;
+    CK(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(int), c->stream));
+    if (haveTrees)
+      LAUNCH(c, k_narrow_tree<false>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
+             c->pairSlot.p, TC, HO, c->pairCap.p, c->counters.p + 1);
+    int nslots = scanTotal(c, c->pairCap, c->pairSlot, np);
+    c->nSlots = nslots;
+    c->hitPos.ensure(3 * (size_t)nslots + 3); c->hitNrm.ensure(3 * (size_t)nslots + 3); c->hitViol.ensure((size_t)nslots + 1);
+    c->hitMeta.ensure(4 * (size_t)nslots + 4);
+    HO = HitOut{c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p};
+    CK(cudaMemsetAsync(c->pairCount.p, 0, (np + 1) * sizeof(int), c->stream));
+    LAUNCH(c, k_narrow_box, nblk(np, 128), 128, np, c->pairValSorted.p, c->pairType.p, c->pairSlot.p, c->shSize.p, c->shRadius.p,
+           c->shX.p, c->shR.p, HO, c->pairCount.p);
+    if (haveTrees)
+      LAUNCH(c, k_narrow_tree<true>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
+             c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1);
+    nc = scanTotal(c, c->pairCount, c->pairOut, np);
+    if (haveTrees && readInt(c, c->counters.p + 1)) throw AmError(AM3D_ECAPACITY, "sphere-tree traversal stack overflow");
+    c->cur.ensure(nc + 1);
+    ContactOut CO{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.bv1.p, c->cur.bv2.p, c->cur.info.p, c->cur.leaf.p,
+                  c->cur.state.p, c->cur.isNew.p, c->cur.key0.p, c->cur.key1.p, c->cur.pW.p, c->cur.nW.p, c->cur.t1W.p,
+                  c->cur.t2W.p, c->cur.pB1.p, c->cur.nB1.p, c->cur.t1B1.p, c->cur.t2B1.p, c->cur.viol.p, c->cur.prevViol.p,
+                  c->cur.lam.p, c->cur.lamWarm.p};
+    LAUNCH(c, k_contact_set, nblk(np, 128), 128, np, c->pairKeySorted.p, c->pairValSorted.p, c->pairSlot.p, c->pairCount.p,
+           c->pairOut.p, c->shBody.p, c->x.p, c->R.p, c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p, CO);
+  }
+  c->cur.n = nc;
+  c->cur.nSorted = nc;
+  c->bpTail = false;
+  c->T.n_contacts = nc;
+}
+
+// updateBodyPairContacts (CollisionProcessor.java:145-164): body pairs of this step, histories carried over
+static void buildBodyPairs(am3d_ctx* c) {
+  int nc = c->cur.n;
+  int nbp = 0;
+  if (nc > 0) {
+    c->tmpI0.ensure(nc + 1); c->tmpI1.ensure(nc + 1);
+    LAUNCH(c, k_bpc_heads, nblk(nc), BLK, nc, c->cur.key0.p, c->cur.b1.p, c->cur.b2.p, c->flags.p, c->tmpI0.p);
+    nbp = scanTotal(c, c->tmpI0, c->tmpI1, nc);
+    c->bp.ensure(nbp + 1);
+    LAUNCH(c, k_bpc_fill, nblk(nc), BLK, nc, c->cur.key0.p, c->tmpI0.p, c->tmpI1.p, c->cur.b1.p, c->cur.b2.p, c->flags.p,
+           c->cur.bpc.p, c->bp.key.p, c->bp.start.p, c->bp.b1.p, c->bp.b2.p);
+    LAUNCH(c, k_bpc_match, nblk(nbp), BLK, nbp, nc, c->bp.key.p, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p,
+           c->bp.nActive.p, c->bp.metricHist.p, c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, c->bp.alive.p,
+           c->bpPrev.n, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p, c->bpPrev.metricHist.p, c->bpPrev.stateHist.p,
+           c->bpPrev.nMetric.p, c->bpPrev.nState.p);
+  }
+  c->bp.n = nbp;
+}
+
+static void warmStart(am3d_ctx* c) {
+  int nbp = c->bp.n;
+  if (nbp == 0) return;
+  WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,
+            c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
+            c->prev.n, c->prev.nSorted, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, c->prev.viol.p, c->prev.lam.p,
+            c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
+  LAUNCH(c, k_warm_start, nblk(nbp, 128), 128, nbp, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p, W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// solve
+// ------------------------------------------------------------------------------------------------

@@ -1,0 +1,350 @@
+// Host orchestration of the two PGS solves (full solve and single sweep) and of merge / unmerge.
+#pragma once
+#include "am3d_host_util.cuh"
+#include "am3d_merge.cuh"
+#include "am3d_step.cuh"
+
+static SolveArrays solveArrays(am3d_ctx* c) {
+  return SolveArrays{c->sgB1.p, c->sgB2.p, c->sgStart.p, c->sgCount.p, c->sgFlags.p, c->sgBpc.p, c->sgMass.p, c->sgMu.p,
+                     c->scD.p, c->scR.p, c->scB.p, c->scDiag.p, c->scLam.p, c->scSrc.p, c->scState.p};
+}
+static ContactPtrs contactPtrs(ContactSet& S) {
+  return ContactPtrs{S.b1.p, S.b2.p, S.s1.p, S.s2.p, S.bv1.p, S.bv2.p, S.info.p, S.leaf.p, S.bpc.p, S.state.p, S.isNew.p,
+                     S.key0.p, S.key1.p, S.pW.p, S.nW.p, S.t1W.p, S.t2W.p, S.pB1.p, S.nB1.p, S.t1B1.p, S.t2B1.p, S.viol.p,
+                     S.prevViol.p, S.lam.p, S.lamWarm.p};
+}
+
+// colour the groups (body pairs) so that no two groups of a colour share a non-pinned solver body
+static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, int inCollection) {
+  c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
+  c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
+  LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, inCollection, c->grpSb1.p, c->grpSb2.p,
+         c->grpPrio.p, c->grpColor.p);
+  CK(cudaMemsetAsync(c->bodyBest.p, 0, c->NS * sizeof(unsigned long long), c->stream));
+  CK(cudaMemsetAsync(c->bodyMask.p, 0, c->NS * sizeof(unsigned long long), c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
+  int page = 0;
+  const int maxPages = 64;
+  while (true) {
+    int remaining = 1, rounds = 0;
+    while (remaining > 0) {
+      for (int r = 0; r < 4; r++) {  // a few rounds per host read-back
+        CK(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(int), c->stream));
+        LAUNCH(c, k_color_bid, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p);
+        LAUNCH(c, k_color_assign, nblk(ng), BLK, ng, page, c->grpSb1.p, c->grpSb2.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p,
+               c->bodyMask.p, c->counters.p + 2, c->counters.p + 3);
+      }
+      remaining = readInt(c, c->counters.p + 2);
+      if (++rounds > 100000) throw AmError(AM3D_ECUDA, "colouring did not converge");
+    }
+    int deferred = readInt(c, c->counters.p + 3);
+    if (deferred == 0) break;
+    if (++page >= maxPages) throw AmError(AM3D_ECAPACITY, "more than 4096 colours needed");
+    CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->bodyMask.p, 0, c->NS * sizeof(unsigned long long), c->stream));
+    LAUNCH(c, k_color_next_page, nblk(ng), BLK, ng, page - 1, c->grpColor.p);
+  }
+  int maxColors = (page + 1) * 64;
+  c->colorHist.ensure(maxColors + 1);
+  CK(cudaMemsetAsync(c->colorHist.p, 0, (maxColors + 1) * sizeof(int), c->stream));
+  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, c->grpKey.p, c->grpVal.p, c->colorHist.p);
+  int endBit = 32 + bitsFor((unsigned long long)maxColors);
+  cubRun(c, [&](void* t, size_t& b) {
+    return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
+  });
+  std::vector<int> hist(maxColors);
+  CK(cudaMemcpyAsync(hist.data(), c->colorHist.p, maxColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->colorStart.clear();
+  int acc = 0;
+  for (int k = 0; k < maxColors; k++) {
+    if (hist[k] == 0) continue;
+    c->colorStart.push_back(acc);
+    acc += hist[k];
+  }
+  c->colorStart.push_back(acc);
+  c->nColors = (int)c->colorStart.size() - 1;
+  c->nGroups = ng;
+}
+
+// One contact set taking part in a solve: its groups start at groupOffset in the group list.
+struct SolveSet {
+  ContactSet* S;
+  int groupOffset;
+  int setId;
+  bool writeLambda;
+};
+
+// PGS.solve (PGS.java:73-194).  sweep = false: the full solve over the external contacts with collections as
+// solver bodies (CollisionProcessor.solveLCP :108-137); sweep = true: the single sweep over external + internal
+// contacts with every body on its own (updateInCollections :232-303).
+static void runSolve(am3d_ctx* c, double dt, bool sweep) {
+  const am3d_params& P = c->P;
+  int nExt = c->bp.n, nInt = sweep ? c->ibp.n : 0;
+  int ng = nExt + nInt;
+  int ncExt = c->cur.n, ncInt = sweep ? c->icon.n : 0;
+  int nc = ncExt + ncInt;
+  if (!sweep) { c->T.pgs_iterations = 0; c->T.pgs_colors = 0; c->T.pgs_kernel_time = 0; }
+  c->lastSolveSweep = sweep;
+  c->lastSolveN = 0;
+  (sweep ? c->orderSweep : c->orderFull).clear();
+  if (nc == 0 || ng == 0) return;
+  const int *gb1, *gb2, *gcount, *gstart;
+  c->swB1.ensure(ng + 1); c->swB2.ensure(ng + 1); c->swCount.ensure(ng + 1); c->swStart.ensure(ng + 1);
+  LAUNCH(c, k_sweep_groups, nblk(ng), BLK, nExt, nInt, c->cur.b1.p, c->cur.b2.p, c->bp.count.p, c->bp.start.p, c->ibp.b1.p,
+         c->icon.b1.p, c->icon.b2.p, c->ibp.count.p, c->ibp.start.p, c->ibp.alive.p, c->parent.p, c->flags.p, c->swB1.p, c->swB2.p,
+         c->swCount.p, c->swStart.p);
+  gb1 = c->swB1.p; gb2 = c->swB2.p; gcount = c->swCount.p; gstart = c->swStart.p;
+  colourGroups(c, ng, gb1, gb2, sweep ? 1 : 0);
+  c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
+  c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1);
+  c->scD.ensure(9 * (size_t)nc + 9); c->scR.ensure(6 * (size_t)nc + 6); c->scB.ensure(3 * (size_t)nc + 3);
+  c->scDiag.ensure(3 * (size_t)nc + 3); c->scLam.ensure(3 * (size_t)nc + 3); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1);
+  SolveArrays S = solveArrays(c);
+  LAUNCH(c, k_group_setup, nblk(ng), BLK, ng, c->grpOrder.p, c->grpSb1.p, c->grpSb2.p, gb1, gb2, gcount, c->minv.p, c->jinv.p,
+         c->fric.p, c->flags.p, P.friction_override, P.friction, S, c->grpPos.p);
+  int nSolve = scanTotal(c, c->sgCount, c->sgStart, ng);  // contacts that take part (sleeping collections excluded)
+  c->lastSolveN = nSolve;
+  SolveSet sets[2] = {{&c->cur, 0, 0, !sweep}, {&c->icon, nExt, 1, true}};
+  int nsets = sweep ? 2 : 1;
+  for (int k = 0; k < nsets; k++) {
+    ContactSet& CS = *sets[k].S;
+    if (CS.n == 0) continue;
+    LAUNCH(c, k_assemble, nblk(CS.n, 128), 128, CS.n, CS.bpc.p, sets[k].groupOffset, sets[k].setId, gstart, gcount, c->grpPos.p,
+           c->sgStart.p, CS.b1.p, CS.b2.p, c->parent.p, sweep ? 1 : 0, CS.pW.p, CS.nW.p, CS.t1W.p, CS.t2W.p, CS.pB1.p, CS.nB1.p,
+           CS.t1B1.p, CS.t2B1.p, CS.viol.p, CS.lam.p, CS.state.p, c->x.p, c->R.p, c->v.p, c->w.p, c->force.p, c->torque.p,
+           c->minv.p, c->jinv.p, c->rest.p, dt, P.feedback_stiffness, P.restitution_override, P.restitution, S);
+  }
+  CK(cudaMemsetAsync(c->iterState.p, 0, 8 * sizeof(unsigned long long), c->stream));
+  PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold};
+  int iterations = sweep ? P.iterations_in_collection : P.iterations;
+  CK(cudaEventRecord(c->ev[sweep ? 8 : 10], c->stream));
+  for (int k = 0; k < c->nColors; k++) {
+    int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
+    LAUNCH(c, k_pgs_color<0>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+  }
+  for (int it = 0; it < iterations; it++) {
+    int last = it == iterations - 1;
+    for (int k = 0; k < c->nColors; k++) {
+      int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
+      LAUNCH(c, k_pgs_color<1>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+      c->solveLaunches++;
+    }
+    LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);
+  }
+  CK(cudaEventRecord(c->ev[sweep ? 9 : 11], c->stream));
+  if (!sweep) CK(cudaMemsetAsync(c->bp.nActive.p, 0, (nExt + 1) * sizeof(int), c->stream));
+  LAUNCH(c, k_post_solve, nblk(nSolve), BLK, nSolve, S, c->cur.bpc.p, c->cur.lam.p, c->cur.state.p, sweep ? 0 : 1,
+         sweep ? (int*)nullptr : c->bp.nActive.p, c->icon.lam.p, c->icon.state.p);
+  if (c->recordOrders) {  // tests: keep the Gauss-Seidel sequence for replay on the CPU oracle
+    std::vector<int>& dst = sweep ? c->orderSweep : c->orderFull;
+    dst.resize(nSolve);
+    if (nSolve) CK(cudaMemcpyAsync(dst.data(), c->scSrc.p, nSolve * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (!sweep) {
+    unsigned long long st[4];
+    CK(cudaMemcpyAsync(st, c->iterState.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->T.pgs_iterations = (int)st[2];
+    c->T.pgs_colors = c->nColors;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]));
+    c->T.pgs_kernel_time = ms * 1e-3;
+    c->rowUpdates += 3.0 * nSolve * (double)st[2];
+    c->solveSeconds += c->T.pgs_kernel_time;
+  } else {
+    CK(cudaStreamSynchronize(c->stream));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// collections: membership CSR + mass properties of the changed ones
+// ------------------------------------------------------------------------------------------------
+static void rebuildMembers(am3d_ctx* c) {
+  int nb = c->NB, nc = c->NS - c->NB;
+  c->memKey.ensure(nb + 1); c->memKeySorted.ensure(nb + 1); c->memVal.ensure(nb + 1); c->members.ensure(nb + 1);
+  c->collCount.ensure(nc + 2); c->collStart.ensure(nc + 2);
+  CK(cudaMemsetAsync(c->collCount.p, 0, (nc + 2) * sizeof(int), c->stream));
+  LAUNCH(c, k_member_keys, nblk(nb), BLK, nb, nc, c->parent.p, c->memKey.p, c->memVal.p, c->collCount.p);
+  cubRun(c, [&](void* t, size_t& b) {
+    return cub::DeviceRadixSort::SortPairs(t, b, c->memKey.p, c->memKeySorted.p, c->memVal.p, c->members.p, nb, 0, bitsFor((unsigned long long)nc + 1), c->stream);
+  });
+  scanTotal(c, c->collCount, c->collStart, nc);
+}
+static int countAlive(am3d_ctx* c) {
+  int nc = c->NS - c->NB;
+  c->tmpI0.ensure(nc + 2); c->tmpI1.ensure(nc + 2);
+  CK(cudaMemcpyAsync(c->tmpI0.p, c->collAlive.p, nc * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  return scanTotal(c, c->tmpI0, c->tmpI1, nc);
+}
+static void recomputeChanged(am3d_ctx* c) {
+  int nc = c->NS - c->NB;
+  rebuildMembers(c);
+  c->tmpI0.ensure(nc + 2); c->tmpI1.ensure(nc + 2); c->changedList.ensure(nc + 2);
+  LAUNCH(c, k_changed_flags, nblk(nc), BLK, nc, c->collAlive.p, c->collMode.p, c->tmpI0.p);
+  int nch = scanTotal(c, c->tmpI0, c->tmpI1, nc);
+  if (nch > 0) {
+    LAUNCH(c, k_changed_list, nblk(nc), BLK, nc, c->tmpI0.p, c->tmpI1.p, c->changedList.p);
+    LAUNCH(c, k_coll_recompute, nch, CR_THREADS, nc, c->NB, c->changedList.p, c->collMode.p, c->collStart.p, c->collCount.p,
+           c->members.p, c->collFlagAcc.p, c->x.p, c->R.p, c->v.p, c->w.p, c->mass.p, c->minv.p, c->mA.p, c->mA0.p, c->jinv.p,
+           c->jinv0.p, c->flags.p, c->bbB.p, c->bbCount.p, c->B2CR.p, c->B2Ct.p);
+  }
+  CK(cudaMemsetAsync(c->collMode.p, 0, nc * sizeof(int), c->stream));
+  c->nCollections = countAlive(c);
+}
+static int freeSlotList(am3d_ctx* c) {
+  int nc = c->NS - c->NB;
+  c->tmpI2.ensure(nc + 2); c->tmpI3.ensure(nc + 2); c->freeList.ensure(nc + 2);
+  LAUNCH(c, k_free_slots, nblk(nc), BLK, nc, c->collAlive.p, c->tmpI2.p);
+  int nfree = scanTotal(c, c->tmpI2, c->tmpI3, nc);
+  LAUNCH(c, k_free_list, nblk(nc), BLK, nc, c->tmpI2.p, c->tmpI3.p, c->freeList.p);
+  return nfree;
+}
+static void logEvents(am3d_ctx* c, int kind, const unsigned long long* dkeys, int n) {
+  if (n <= 0) return;
+  std::vector<unsigned long long> k(n);
+  CK(cudaMemcpyAsync(k.data(), dkeys, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) {
+    c->events.push_back(c->totalSteps); c->events.push_back(kind);
+    c->events.push_back((int)(k[i] >> 24)); c->events.push_back((int)(k[i] & 0xffffff));
+  }
+}
+
+// Merging.merge (Merging.java:73-163)
+static void mergeStep(am3d_ctx* c) {
+  const am3d_params& P = c->P;
+  if (!P.enable_merging) return;
+  int nbp = c->bp.n;
+  if (nbp == 0) return;
+  int ns = c->NS, nb = c->NB, nc = ns - nb;
+  c->uf.ensure(ns + 1); c->mflag.ensure(nbp + 2);
+  LAUNCH(c, k_uf_init, nblk(ns), BLK, ns, c->uf.p);
+  CK(cudaMemsetAsync(c->counters.p + 4, 0, sizeof(int), c->stream));
+  MergeParamsD MP{P.merge_pinned, P.merge_stable_contact, P.merge_let_it_breathe, P.step_accum_merging, P.threshold_merge, P.threshold_breath};
+  LAUNCH(c, k_merge_flag, nblk(nbp, 128), 128, nbp, c->bp.alive.p, c->bp.b1.p, c->bp.b2.p, c->bp.start.p, c->bp.count.p, c->cur.lam.p,
+         c->cur.viol.p, c->cur.prevViol.p, c->flags.p, c->parent.p, c->bp.metricHist.p, c->bp.stateHist.p, c->bp.nMetric.p,
+         c->bp.nState.p, MP, c->mflag.p, c->uf.p, c->counters.p + 4);
+  int nFlagged = readInt(c, c->counters.p + 4);
+  if (nFlagged == 0) return;
+  c->mergingEvent = true;
+  LAUNCH(c, k_uf_flatten, nblk(ns), BLK, ns, c->uf.p);
+  c->compEnt.ensure(ns + 2); c->compBest.ensure(ns + 2); c->needNew.ensure(ns + 2); c->newScan.ensure(ns + 2); c->target.ensure(ns + 2);
+  CK(cudaMemsetAsync(c->compEnt.p, 0, ns * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->compBest.p, 0, ns * sizeof(unsigned long long), c->stream));
+  LAUNCH(c, k_merge_census, nblk(ns), BLK, ns, nb, c->collAlive.p, c->parent.p, c->uf.p, c->collCount.p, c->stamp.p, c->compEnt.p, c->compBest.p);
+  LAUNCH(c, k_merge_neednew, nblk(ns), BLK, ns, c->uf.p, c->compEnt.p, c->compBest.p, c->needNew.p);
+  int nNew = scanTotal(c, c->needNew, c->newScan, ns);
+  int nfree = freeSlotList(c);
+  if (nNew > nfree) throw AmError(AM3D_ECAPACITY, "out of collection slots");
+  LAUNCH(c, k_merge_target, nblk(ns), BLK, ns, nb, c->uf.p, c->compEnt.p, c->compBest.p, c->needNew.p, c->newScan.p, c->freeList.p,
+         c->stamp.p, c->collAlive.p, c->target.p);
+  LAUNCH(c, k_merge_target2, nblk(nc), BLK, nc, nb, c->collAlive.p, c->uf.p, c->collCount.p, c->stamp.p, c->compBest.p, c->target.p);
+  CK(cudaMemsetAsync(c->collFlagAcc.p, 0, nc * sizeof(int), c->stream));
+  LAUNCH(c, k_merge_newcolls, nblk(ns), BLK, ns, nb, c->uf.p, c->compEnt.p, c->target.p, c->needNew.p, c->newScan.p, c->collAlive.p,
+         c->flags.p, c->stamp.p, c->nextStamp, c->collMode.p, c->metricCount.p);
+  LAUNCH(c, k_merge_apply, nblk(ns), BLK, ns, nb, c->collAlive.p, c->parent.p, c->uf.p, c->compEnt.p, c->target.p, c->needNew.p,
+         c->newScan.p, c->flags.p, c->stamp.p, c->nextStamp, c->collMode.p, c->collFlagAcc.p, c->metricCount.p);
+  c->nextStamp += nNew;
+  recomputeChanged(c);
+  // every live external pair whose two bodies now share a collection becomes internal
+  c->tmpI0.ensure(nbp + 2); c->tmpI1.ensure(nbp + 2); c->tmpI2.ensure(nbp + 2); c->tmpI3.ensure(nbp + 2);
+  LAUNCH(c, k_int_flag, nblk(nbp), BLK, nbp, c->bp.alive.p, c->bp.b1.p, c->bp.b2.p, c->parent.p, c->bp.nActive.p, c->tmpI0.p, c->tmpI2.p);
+  int nIntB = scanTotal(c, c->tmpI0, c->tmpI1, nbp);
+  int nIntC = scanTotal(c, c->tmpI2, c->tmpI3, nbp);
+  if (nIntB > 0) {
+    c->ibp.ensureKeep(c->ibp.n + nIntB + 1, c->ibp.n, c->stream);
+    c->ibpCut.ensure(c->ibp.n + nIntB + 1, true, c->stream);
+    c->icon.ensureKeep(c->icon.n + nIntC + 1, c->icon.n, c->stream);
+    LAUNCH(c, k_int_copy, nblk(nbp, 128), 128, nbp, c->tmpI0.p, c->tmpI1.p, c->tmpI3.p, c->bp.key.p, c->bp.b1.p, c->bp.b2.p, c->bp.start.p,
+           c->bp.count.p, contactPtrs(c->cur), c->ibp.n, c->icon.n, c->ibp.key.p, c->ibp.b1.p, c->ibp.b2.p, c->ibp.start.p, c->ibp.count.p,
+           c->ibp.alive.p, c->ibp.nMetric.p, c->ibpCut.p, contactPtrs(c->icon));
+    logEvents(c, 0, c->ibp.key.p + c->ibp.n, nIntB);
+    c->ibp.n += nIntB;
+    c->icon.n += nIntC;
+  }
+}
+
+// Merging.unmerge (Merging.java:215-273); returns true if anything was split
+static bool unmergeStep(am3d_ctx* c) {
+  const am3d_params& P = c->P;
+  if (!P.enable_unmerging) return false;
+  if (!P.unmerge_relative_motion && !P.unmerge_normal && !P.unmerge_friction) return false;
+  int nib = c->ibp.n;
+  if (nib == 0 || c->nCollections == 0) return false;
+  int ns = c->NS, nb = c->NB, nc = ns - nb;
+  c->ibpCut.ensure(nib + 1, true, c->stream);
+  c->collCuts.ensure(nc + 2); c->collNComp.ensure(nc + 2); c->collKeeps.ensure(nc + 2);
+  CK(cudaMemsetAsync(c->collCuts.p, 0, nc * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 5, 0, sizeof(int), c->stream));
+  LAUNCH(c, k_unm_flag, nblk(nib, 128), 128, nib, c->ibp.alive.p, c->ibp.b1.p, c->ibp.b2.p, c->ibp.start.p, c->ibp.count.p, c->icon.state.p,
+         c->parent.p, c->flags.p, c->x.p, c->R.p, c->v.p, c->w.p, c->bbB.p, c->bbCount.p, nb, P.threshold_unmerge, P.step_accum_unmerging,
+         P.unmerge_normal, P.unmerge_friction, c->ibp.nMetric.p, c->ibpCut.p, c->collCuts.p, c->counters.p + 5);
+  int nCuts = readInt(c, c->counters.p + 5);
+  if (nCuts == 0) return false;
+  c->uf.ensure(ns + 1);
+  LAUNCH(c, k_uf_init, nblk(nb), BLK, nb, c->uf.p);
+  LAUNCH(c, k_unm_union, nblk(nib), BLK, nib, c->ibp.alive.p, c->ibpCut.p, c->ibp.b1.p, c->ibp.b2.p, c->parent.p, c->collCuts.p, nb, c->uf.p);
+  LAUNCH(c, k_uf_flatten, nblk(nb), BLK, nb, c->uf.p);
+  c->compEnt.ensure(ns + 2); c->needNew.ensure(ns + 2); c->newScan.ensure(ns + 2); c->target.ensure(ns + 2);
+  c->leavesFlag.ensure(nb + 2); c->leavesScan.ensure(nb + 2); c->freedFlag.ensure(nb + 2);
+  CK(cudaMemsetAsync(c->compEnt.p, 0, nb * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->collNComp.p, 0, nc * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->collKeeps.p, 0, nc * sizeof(int), c->stream));
+  LAUNCH(c, k_unm_census, nblk(nb), BLK, nb, c->parent.p, c->collCuts.p, c->uf.p, c->compEnt.p, c->collNComp.p);
+  LAUNCH(c, k_unm_roots, nblk(nb), BLK, nb, c->parent.p, c->collCuts.p, c->uf.p, c->compEnt.p, c->collNComp.p, c->collCount.p,
+         c->leavesFlag.p, c->needNew.p, c->freedFlag.p, c->collKeeps.p);
+  int nLeaving = scanTotal(c, c->leavesFlag, c->leavesScan, nb);
+  bool split = nLeaving > 0;
+  if (split) {
+    c->mergingEvent = true;
+    int nNew = scanTotal(c, c->needNew, c->newScan, nb);
+    int nfree = freeSlotList(c);
+    if (nNew > nfree) throw AmError(AM3D_ECAPACITY, "out of collection slots");
+    CK(cudaMemsetAsync(c->collFlagAcc.p, 0, nc * sizeof(int), c->stream));
+    // list position of the leaving pieces (Merging.java:269: bodies.addAll(additionQueue))
+    c->grpKey.ensure(nb + 2); c->grpKeySorted.ensure(nb + 2); c->tmpI0.ensure(nb + 2); c->tmpI1.ensure(nb + 2);
+    LAUNCH(c, k_unm_rank_keys, nblk(nb), BLK, nb, c->leavesFlag.p, c->parent.p, c->stamp.p, c->grpKey.p, c->tmpI0.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->tmpI0.p, c->tmpI1.p, nb, 0, 64, c->stream);
+    });
+    LAUNCH(c, k_unm_rank_scatter, nblk(nLeaving), BLK, nLeaving, c->tmpI1.p, c->leavesScan.p);
+    LAUNCH(c, k_unm_apply, nblk(nb), BLK, nb, c->parent.p, c->collCuts.p, c->uf.p, c->leavesFlag.p, c->needNew.p, c->newScan.p, c->freeList.p,
+           c->leavesScan.p, c->x.p, c->v.p, c->w.p, c->dv.p, c->stamp.p, c->nextStamp, c->collAlive.p, c->collMode.p, c->flags.p,
+           c->metricCount.p);
+    c->nextStamp += nLeaving;
+    LAUNCH(c, k_unm_retire, nblk(nc), BLK, nc, c->collCuts.p, c->collNComp.p, c->collKeeps.p, c->collAlive.p, c->collMode.p);
+    recomputeChanged(c);
+  }
+  // cut pairs: reconnect or hand back to the external set together with their contacts (Merging.java:343-360)
+  c->tmpI0.ensure(nib + 2); c->tmpI1.ensure(nib + 2); c->tmpI2.ensure(nib + 2); c->tmpI3.ensure(nib + 2);
+  LAUNCH(c, k_unm_reext_flag, nblk(nib), BLK, nib, c->ibp.alive.p, c->ibpCut.p, c->ibp.b1.p, c->ibp.b2.p, c->ibp.count.p, c->parent.p,
+         c->tmpI0.p, c->tmpI2.p);
+  int nExtB = scanTotal(c, c->tmpI0, c->tmpI1, nib);
+  int nExtC = scanTotal(c, c->tmpI2, c->tmpI3, nib);
+  if (nExtB > 0) {
+    c->bp.ensureKeep(c->bp.n + nExtB + 1, c->bp.n, c->stream);
+    c->cur.ensureKeep(c->cur.n + nExtC + 1, c->cur.n, c->stream);
+    LAUNCH(c, k_unm_reext_copy, nblk(nib, 128), 128, nib, c->tmpI0.p, c->tmpI1.p, c->tmpI3.p, c->ibp.key.p, c->ibp.b1.p, c->ibp.b2.p,
+           c->ibp.start.p, c->ibp.count.p, c->ibp.alive.p, contactPtrs(c->icon), c->bp.n, c->cur.n, c->bp.key.p, c->bp.b1.p, c->bp.b2.p,
+           c->bp.start.p, c->bp.count.p, c->bp.alive.p, c->bp.nActive.p, c->bp.nMetric.p, c->bp.nState.p, contactPtrs(c->cur), c->x.p, c->R.p);
+    logEvents(c, 1, c->bp.key.p + c->bp.n, nExtB);
+    c->bp.n += nExtB;
+    c->cur.n += nExtC;
+    c->bpTail = true;
+    // compact the internal tables
+    LAUNCH(c, k_ibp_compact_flag, nblk(nib), BLK, nib, c->ibp.alive.p, c->ibp.count.p, c->tmpI0.p, c->tmpI2.p);
+    int keepB = scanTotal(c, c->tmpI0, c->tmpI1, nib);
+    int keepC = scanTotal(c, c->tmpI2, c->tmpI3, nib);
+    c->ibp2.ensure(keepB + 1); c->icon2.ensure(keepC + 1); c->ibpCut2.ensure(keepB + 1);
+    LAUNCH(c, k_ibp_compact, nblk(nib, 128), 128, nib, c->tmpI0.p, c->tmpI1.p, c->tmpI3.p, c->ibp.key.p, c->ibp.b1.p, c->ibp.b2.p, c->ibp.start.p,
+           c->ibp.count.p, c->ibp.nMetric.p, contactPtrs(c->icon), c->ibp2.key.p, c->ibp2.b1.p, c->ibp2.b2.p, c->ibp2.start.p, c->ibp2.count.p,
+           c->ibp2.alive.p, c->ibp2.nMetric.p, c->ibpCut2.p, contactPtrs(c->icon2));
+    std::swap(c->ibp, c->ibp2);
+    std::swap(c->icon, c->icon2);
+    std::swap(c->ibpCut, c->ibpCut2);
+    c->ibp.n = keepB;
+    c->icon.n = keepC;
+  }
+  return split;
+}

@@ -1,0 +1,63 @@
+// Host-side helpers shared by the orchestration code (launch macro, CUB wrappers, small read-backs).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+
+#include "am3d_ctx.h"
+#include "am3d_math.cuh"
+
+static bool amTrace() { static int t = -1; if (t < 0) t = getenv("AM3D_TRACE") ? 1 : 0; return t == 1; }
+#define LAUNCH(ctx, kernel, grid, block, ...)                  \
+  do {                                                         \
+    if (amTrace()) fprintf(stderr, "[am3d] %s grid=%d\n", #kernel, (int)(grid)); \
+    if ((grid) > 0) {                                          \
+      kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__); \
+      (ctx)->kernelLaunches++;                                 \
+      cudaError_t _le = cudaGetLastError();                    \
+      if (_le != cudaSuccess) throw AmError(AM3D_ECUDA, std::string("launch of " #kernel ": ") + cudaGetErrorString(_le)); \
+    }                                                          \
+  } while (0)
+
+template <class F>
+static void cubRun(am3d_ctx* c, F f) {
+  size_t bytes = 0;
+  CK(f(nullptr, bytes));
+  c->cubTemp.ensure(bytes + 16);
+  CK(f(c->cubTemp.p, bytes));
+  c->kernelLaunches++;
+}
+
+template <class T>
+static void h2d(am3d_ctx* c, DevBuf<T>& d, const T* src, size_t n) {
+  d.ensure(n ? n : 1);
+  if (n) CK(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+}
+template <class T>
+static void h2dv(am3d_ctx* c, DevBuf<T>& d, const std::vector<T>& v) { h2d(c, d, v.data(), v.size()); }
+
+static int readInt(am3d_ctx* c, const int* p) {
+  int v;
+  CK(cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return v;
+}
+
+// exclusive scan of n ints (+ a trailing 0) so that out[n] is the total
+static int scanTotal(am3d_ctx* c, DevBuf<int>& in, DevBuf<int>& out, int n) {
+  out.ensure(n + 1);
+  CK(cudaMemsetAsync(in.p + n, 0, sizeof(int), c->stream));
+  cubRun(c, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, in.p, out.p, n + 1, c->stream); });
+  return readInt(c, out.p + n);
+}
+
+static int bitsFor(unsigned long long v) {
+  int b = 1;
+  while ((v >> b) && b < 63) b++;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene upload / reset

@@ -192,8 +192,8 @@ struct WarmCtx {
   const double* pB1;
   double *lam, *lamWarm, *prevViol;
   int* isNew;
-  // previous
-  int np;
+  // previous (entries [0,npSorted) are in canonical key order, [npSorted,np) were appended by an unmerge)
+  int np, npSorted;
   const unsigned long long *pkey0, *pkey1;
   const int *pb1, *pleaf;
   const double *ppB1, *pviol;
@@ -206,7 +206,7 @@ struct WarmCtx {
 
 // find the previous contact equal to (key0, key1); duplicate keys (box x tree leaf hits, Appendix B):
 // the reference's HashMap keeps the LAST one put, i.e. the last in DFS emission order = largest node rank
-__device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsigned long long k1) {
+__device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsigned long long k0, unsigned long long k1) {
   int best = -1, bestRank = -1;
   for (int j = lo; j < hi; j++) {
     if (W.pkey1[j] == k1) {
@@ -214,6 +214,9 @@ __device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsi
       int rk = lf >= 0 ? W.ndRank[lf] : 0;
       if (best < 0 || rk > bestRank) { best = j; bestRank = rk; }
     }
+  }
+  for (int j = W.npSorted; j < W.np; j++) {  // appended later in the list: they win over earlier duplicates
+    if (W.pkey0[j] == k0 && W.pkey1[j] == k1) { best = j; bestRank = 0x7fffffff; }
   }
   return best;
 }
@@ -244,10 +247,10 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
   for (int i = s; i < e; i++) {
     unsigned long long k0 = W.key0[i], k1 = W.key1[i];
     // range of previous contacts with the same (bodyLo, bodyHi, partLo, partHi)
-    int lo = 0, hi = W.np;
+    int lo = 0, hi = W.npSorted;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] < k0) lo = mid + 1; else hi = mid; }
     int rlo = lo;
-    hi = W.np;
+    hi = W.npSorted;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] <= k0) lo = mid + 1; else hi = mid; }
     int rhi = lo;
     bool vanillaOnly = !boxy;
@@ -260,14 +263,14 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
       else if (nb2) { vanillaOnly = true; doBox = true; }  // vanilla, then falls through into the box-box repair
     }
     if (vanillaOnly) {
-      int j = warmLookup(W, rlo, rhi, k1);
+      int j = warmLookup(W, rlo, rhi, k0, k1);
       if (j >= 0) warmTake(W, i, j, false); else W.isNew[i] = 1;
     }
     if (!doBox) continue;
     d3 pNew = worldPoint(W.x, W.R, W.b1[i], ld3(W.pB1 + 3 * i));
     int myInfo = (int)(k1 & 0xff);
     unsigned long long kbase = k1 & ~0xffULL;
-    int j = warmLookup(W, rlo, rhi, k1);
+    int j = warmLookup(W, rlo, rhi, k0, k1);
     if (j >= 0) {
       d3 pOld = worldPoint(W.x, W.R, W.pb1[j], ld3(W.ppB1 + 3 * j));
       double dist = vdist(pNew, pOld);
@@ -276,7 +279,7 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
         int bestJ = j;
         for (int info = 0; info < 9; info++) {
           if (info == myInfo) continue;
-          int jj = warmLookup(W, rlo, rhi, kbase | (unsigned long long)info);
+          int jj = warmLookup(W, rlo, rhi, k0, kbase | (unsigned long long)info);
           if (jj < 0) break;
           pOld = worldPoint(W.x, W.R, W.pb1[jj], ld3(W.ppB1 + 3 * jj));
           dist = vdist(pNew, pOld);
@@ -290,7 +293,7 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
       double bestDist = 1.7976931348623157e308;
       int bestJ = -1;
       for (int info = 0; info < 9; info++) {
-        int jj = warmLookup(W, rlo, rhi, kbase | (unsigned long long)info);
+        int jj = warmLookup(W, rlo, rhi, k0, kbase | (unsigned long long)info);
         if (jj < 0) break;
         d3 pOld = worldPoint(W.x, W.R, W.pb1[jj], ld3(W.ppB1 + 3 * jj));
         double dist = vdist(pNew, pOld);
@@ -539,8 +542,10 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
 // Contact.computeJacobian :235-271, computeB :279-326, computeJMinvJt :340-354; one thread per contact,
 // output in solve order.  Body state is read through the solver-body index (collection parent unless
 // inCollection).
-__global__ void k_assemble(int nc, const int* __restrict__ cbpc, const int* __restrict__ gstart /* bpc -> first contact */,
-                           const int* __restrict__ grpPos, const int* __restrict__ sgStart, const int* __restrict__ cb1,
+__global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset, int setId,
+                           const int* __restrict__ gstart /* group -> first contact in its set */,
+                           const int* __restrict__ gcount, const int* __restrict__ grpPos,
+                           const int* __restrict__ sgStart, const int* __restrict__ cb1,
                            const int* __restrict__ cb2, const int* __restrict__ parent, int inCollection,
                            const double* __restrict__ pW, const double* __restrict__ nW, const double* __restrict__ t1W,
                            const double* __restrict__ t2W, const double* __restrict__ pB1, const double* __restrict__ nB1,
@@ -554,6 +559,8 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, const int* __re
   if (i >= nc) return;
   int g = cbpc[i];
   if (g < 0) return;
+  g += groupOffset;
+  if (gcount[g] == 0) return;  // internal pair of a sleeping collection: not part of the sweep
   int idx = sgStart[grpPos[g]] + (i - gstart[g]);
   int l1 = cb1[i], l2 = cb2[i];
   int a = l1, b = l2;
@@ -623,7 +630,7 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, const int* __re
     S.scDiag[3 * idx + k] = mi1 * vdot(jav, jav) + vdot(jaw[k], tmp1) + mi2 * vdot(dir[k], dir[k]) + vdot(jbw[k], tmp2);
     S.scLam[3 * idx + k] = lam[3 * i + k];
   }
-  S.scSrc[idx] = i;
+  S.scSrc[idx] = i | (setId << 30);
   S.scState[idx] = cstate[i];
 }
 
@@ -746,16 +753,24 @@ __global__ void k_iter_end(unsigned long long* iterState, double tolerance, int 
   iterState[0] = 0;
 }
 
-// copy the solution back to canonical contact order and count active contacts per body pair
-__global__ void k_post_solve(int nc, SolveArrays S, const int* __restrict__ cbpc, double* __restrict__ lam,
-                             int* __restrict__ cstate, int* __restrict__ nActive) {
+// copy the solution back to the contact sets (set 0 = external, set 1 = internal contacts of collections) and
+// count active contacts per external body pair
+__global__ void k_post_solve(int nc, SolveArrays S, const int* __restrict__ cbpc0, double* __restrict__ lam0,
+                             int* __restrict__ state0, int writeLam0, int* __restrict__ nActive, double* __restrict__ lam1,
+                             int* __restrict__ state1) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nc) return;
-  int i = S.scSrc[idx];
+  int src = S.scSrc[idx];
+  int set = src >> 30, i = src & 0x3fffffff;
   double l0 = S.scLam[3 * idx];
-  lam[3 * i] = l0; lam[3 * i + 1] = S.scLam[3 * idx + 1]; lam[3 * i + 2] = S.scLam[3 * idx + 2];
-  cstate[i] = S.scState[idx];
-  if (nActive && cbpc[i] >= 0 && fabs(l0) > 1e-14) atomicAdd(nActive + cbpc[i], 1);  // clearBodyPairContacts :213-226
+  if (set == 0) {
+    if (writeLam0) { lam0[3 * i] = l0; lam0[3 * i + 1] = S.scLam[3 * idx + 1]; lam0[3 * i + 2] = S.scLam[3 * idx + 2]; }
+    state0[i] = S.scState[idx];
+    if (nActive && cbpc0[i] >= 0 && fabs(l0) > 1e-14) atomicAdd(nActive + cbpc0[i], 1);  // clearBodyPairContacts :213-226
+  } else {
+    lam1[3 * i] = l0; lam1[3 * i + 1] = S.scLam[3 * idx + 1]; lam1[3 * i + 2] = S.scLam[3 * idx + 2];
+    state1[i] = S.scState[idx];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -816,6 +831,16 @@ __global__ void k_advance_positions(int ns, int nb, const int* __restrict__ aliv
   stm(mA + 9 * i, rm0rt(Rm, ldm(mA0 + 9 * i)));
   stm(jinv + 9 * i, rm0rt(Rm, ldm(jinv0 + 9 * i)));
 }
+__global__ void k_update_inertia(int nb, const int* __restrict__ flags, const double* __restrict__ R,
+                                 const double* __restrict__ jinv0, const double* __restrict__ mA0,
+                                 double* __restrict__ jinv, double* __restrict__ mA) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  if (flags[i] & AM3D_F_PINNED) return;
+  m3 Rm = ldm(R + 9 * i);
+  stm(mA + 9 * i, rm0rt(Rm, ldm(mA0 + 9 * i)));
+  stm(jinv + 9 * i, rm0rt(Rm, ldm(jinv0 + 9 * i)));
+}
 __global__ void k_viscous(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
                           double* __restrict__ v, double* __restrict__ w, double a1, double a2) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -841,9 +866,6 @@ __global__ void k_bpc_accumulate(int nbp, const int* __restrict__ bb1, const int
   if (nActive[b] == 0) { alive[b] = 0; return; }  // removeEmptyBodyPairContacts :191-208
   int l1 = bb1[b], l2 = bb2[b];
   int a = parent[l1] >= 0 ? parent[l1] : l1, c = parent[l2] >= 0 ? parent[l2] : l2;
-  if (!((flags[l1] & AM3D_F_PINNED) || (flags[l2] & AM3D_F_PINNED))) {
-    hasExt[l1] = 1; hasExt[l2] = 1; hasExt[a] = 1; hasExt[c] = 1;
-  }
   if (accum > 4) accum = 4;
   double m = pairMetric(a, c, flags, x, R, v, w, bbB, bbCount);
   int n = nm[b];
@@ -883,4 +905,33 @@ __global__ void k_bpc_compact(int nbp, const int* __restrict__ alive, const int*
   okey[o] = key[b]; ob1[o] = b1[b]; ob2[o] = b2[b]; onm[o] = nm[b]; onst[o] = nst[b];
 #pragma unroll
   for (int k = 0; k < 4; k++) { omh[4 * o + k] = mh[4 * b + k]; osh[4 * o + k] = sh[4 * b + k]; }
+}
+
+__global__ void k_iota(int n, int* __restrict__ a) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = i;
+}
+__global__ void k_bpc_gather(int n, const int* __restrict__ src, const unsigned long long* __restrict__ key,
+                             const int* __restrict__ b1, const int* __restrict__ b2, const double* __restrict__ mh,
+                             const int* __restrict__ sh, const int* __restrict__ nm, const int* __restrict__ nst,
+                             unsigned long long* __restrict__ okey, int* __restrict__ ob1, int* __restrict__ ob2,
+                             double* __restrict__ omh, int* __restrict__ osh, int* __restrict__ onm, int* __restrict__ onst) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  int b = src[o];
+  okey[o] = key[b]; ob1[o] = b1[b]; ob2[o] = b2[b]; onm[o] = nm[b]; onst[o] = nst[b];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { omh[4 * o + k] = mh[4 * b + k]; osh[4 * o + k] = sh[4 * b + k]; }
+}
+
+// Sleeping.sleep :64-72: does a top-level body still have an external, non-pinned body pair?  Evaluated after
+// Merging.merge, when pairs that just became internal no longer count.
+__global__ void k_has_ext(int nbp, const int* __restrict__ alive, const int* __restrict__ bb1, const int* __restrict__ bb2,
+                          const int* __restrict__ parent, const int* __restrict__ flags, int* __restrict__ hasExt) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp || !alive[b]) return;
+  int l1 = bb1[b], l2 = bb2[b];
+  if ((flags[l1] & AM3D_F_PINNED) || (flags[l2] & AM3D_F_PINNED)) return;
+  int a = parent[l1] >= 0 ? parent[l1] : l1, c = parent[l2] >= 0 ? parent[l2] : l2;
+  hasExt[l1] = 1; hasExt[l2] = 1; hasExt[a] = 1; hasExt[c] = 1;
 }

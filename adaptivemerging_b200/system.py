@@ -161,6 +161,47 @@ class RigidBodySystem:
         self._ck(self._L.am3d_stats(self._h, _p(out)))
         return dict(kernel_launches=int(out[0]), solve_launches=int(out[1]), row_updates=out[2], solve_seconds=out[3])
 
+    def events(self):
+        """Merge / unmerge decisions so far: rows (step, kind, bodyLo, bodyHi); kind 0 = pair became internal to a
+        collection (Merging.merge), 1 = pair left its collection (Merging.unmerge)."""
+        n = self._L.am3d_num_events(self._h)
+        out = np.zeros((max(n, 1), 4), np.int32)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_events(self._h, _p(out), n, C.byref(cnt)))
+        return out[:cnt.value]
+
+    def record_orders(self, on=True):
+        self._ck(self._L.am3d_record_orders(self._h, int(on)))
+
+    def order(self, which):
+        """Gauss-Seidel sequence (contact identities) of the last full solve (0) / single sweep (1)."""
+        cap = self._L.am3d_num_contacts(self._h, 1) + 1
+        out = np.zeros(cap, CONTACT_DTYPE)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_order(self._h, int(which), _p(out), cap, C.byref(cnt)))
+        return out[:cnt.value]
+
+    def internal_bpcs(self):
+        n = self._L.am3d_num_internal_bpcs(self._h)
+        out = np.zeros(max(n, 1), BPC_DTYPE)
+        cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_internal_bpcs(self._h, _p(out), n, C.byref(cnt)))
+        return out[:cnt.value]
+
+    def collection(self, slot):
+        out = np.zeros(42)
+        self._ck(self._L.am3d_download_collection(self._h, int(slot), _p(out)))
+        return dict(x=out[0:3], R=out[3:12], v=out[12:15], omega=out[15:18], mass=out[18], minv=out[19], jinv=out[20:29],
+                    mA=out[29:38], flags=int(out[38]), alive=int(out[39]), count=int(out[40]), stamp=int(out[41]))
+
+    def mark(self, slot):
+        self._ck(self._L.am3d_mark(self._h, int(slot)))
+
+    def elapsed_ms(self):
+        ms = C.c_double(0)
+        self._ck(self._L.am3d_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
     # -- phase-level entry points (parity tests, roofline leg of bench.py) ------------------------------
     def detect(self):
         self._ck(self._L.am3d_detect(self._h))

@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the AdaptiveMerging 3D rigid-body step on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload stack|pile|batch] [--impl reference]
+
+One "step" = one RigidBodySystem.advanceTime(0.05) over the whole workload.  For N > 1 the driver launches
+one process per GPU with torch.distributed; every rank steps its own shard of independent scenes (weak
+scaling, no data-path collective), the timed region is bracketed by barrier + synchronize and the MAX over
+ranks is reported.  Rank 0 prints ONE JSON line.
+
+  value        body-steps/s with the state resident in HBM (device time of K steps, CUDA events on the
+               library's own stream)
+  e2e          the same metric through the public call with HOST buffers: every step uploads the body
+               state from pinned host memory, steps, and downloads the body state
+  roofline     PGS sweep kernel: 752 B per contact per iteration / measured sweep time,
+               against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the CPU oracle (a single-threaded restatement of the reference's Java step) on a bounded
+               sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+PGS_BYTES_PER_CONTACT_ITER = 752.0
+METRIC = "body_steps_per_s"
+UNIT = "body-steps/s"
+
+
+def build_workload(name, size):
+    """Returns (blob, params, description).  Sizes are per GPU."""
+    from adaptivemerging_b200.ctypes_defs import apply_overrides, default_params
+    from adaptivemerging_b200.scene import box_stack
+    p = default_params()
+    if name in ("stack", "pile"):
+        n = size or 100
+        ny = n
+        blob = box_stack(n, ny, n, pile=(name == "pile"))
+        p.enable_merging = 0  # TODO(merging on GPU): config M is quoted with merging on and off
+        return blob, p, f"{name} {n}x{ny}x{n} unit boxes on a plane (config M of BASELINE.json), merging off"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def sample_workload(name):
+    """Bounded CPU sample of the same workload (the reference's broadphase is O(N^2))."""
+    from adaptivemerging_b200.scene import box_stack
+    if name in ("stack", "pile"):
+        return box_stack(12, 100, 12, pile=(name == "pile")), "12x100x12 = 14,400 boxes of the same stack"
+    raise SystemExit(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            t = [s.strip() for s in ln.split(",")]
+            if len(t) < 7:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if t[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  No JVM exists on the box, so
+    this is the single-threaded C++ restatement under oracle/ (kind = "port"), on a bounded sample."""
+    if rank != 0:
+        return
+    from adaptivemerging_b200.ctypes_defs import default_params
+    from oracle.oracle import Oracle
+    blob, sample = sample_workload(args.workload)
+    p = default_params()
+    p.enable_merging = 0
+    o = Oracle(blob, p)
+    nb = blob.n_bodies - 1
+    for _ in range(args.warmup):
+        o.step(0.05)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.step(0.05)
+    dt = time.perf_counter() - t0
+    val = nb * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": sample, "dt": 0.05},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pgs_row_updates_per_s": o.row_updates() / max(o.solve_seconds(), 1e-12)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="stack")
+    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--settle", type=int, default=20, help="untimed steps before the warm-up so that contacts exist")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("no CUDA device: the rigid-body step has no CPU fallback")
+
+    from adaptivemerging_b200.system import RigidBodySystem
+    blob, params, desc = build_workload(args.workload, args.size)
+    nb = int((blob.a["body_type"] != 1).sum())  # non-plane leaf bodies
+    sysm = RigidBodySystem(local).load(blob, params)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.settle + args.warmup):
+        sysm.advanceTime(0.05)
+
+    # ---- resident-state leg -------------------------------------------------------------------
+    s0 = sysm.stats()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    sysm.mark(0)
+    t0 = time.perf_counter()
+    contacts = iters = 0
+    for _ in range(args.steps):
+        sysm.advanceTime(0.05)
+        t = sysm.timings()
+        contacts += t.n_contacts
+        iters += t.pgs_iterations
+    sysm.mark(1)
+    ms = sysm.elapsed_ms()
+    barrier()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    s1 = sysm.stats()
+    tm = sysm.timings()
+
+    # ---- end-to-end leg: host buffers in, host buffers out, every step ------------------------------
+    b = sysm.bodies()
+    n = sysm.n_bodies
+    host = {k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ("x", "R", "v", "omega")}
+    hnp = {k: host[k].numpy() for k in host}
+    h2d = sum(hnp[k].nbytes for k in hnp)
+    d2h = h2d + 2 * 4 * n
+    barrier()
+    sysm.mark(0)
+    for _ in range(args.steps):
+        sysm.upload_bodies(hnp["x"], hnp["R"], hnp["v"], hnp["omega"])
+        sysm.advanceTime(0.05)
+        nb_ = sysm.bodies()
+        for k in hnp:
+            hnp[k][...] = nb_[k]
+    sysm.mark(1)
+    ms_e2e = sysm.elapsed_ms()
+    barrier()
+
+    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    counts = torch.tensor([float(nb), float(s1["row_updates"] - s0["row_updates"]), float(s1["solve_seconds"] - s0["solve_seconds"]),
+                           float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        tot = counts.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    else:
+        tot = counts
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms, ms_e2e = float(times[0]), float(times[1])
+    total_bodies = float(tot[0])
+    value = total_bodies * args.steps / (ms * 1e-3)
+    e2e = total_bodies * args.steps / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel (rank 0's PGS sweeps)
+    row_updates = float(counts[1])
+    solve_s = float(counts[2])
+    peak, peak_src = hbm_peak()
+    achieved = (row_updates / 3.0) * PGS_BYTES_PER_CONTACT_ITER / max(solve_s, 1e-12) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "bodies_per_gpu": nb, "dt": 0.05,
+                   "pgs_iterations": params.iterations, "settle_steps": args.settle,
+                   "l2": "working set (body + contact arrays) exceeds the 126 MB L2" if nb >= 200000 else
+                         "working set fits L2; no flush between steps (steps are data dependent)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(float(tot[3])),
+        "clocks": clk,
+        "pgs_row_updates_per_s": float(tot[1]) / max(solve_s, 1e-12) if world == 1 else float(tot[1]) / max(solve_s, 1e-12),
+        "contacts_last_step": tm.n_contacts, "pairs_last_step": tm.n_pairs, "pgs_colors": tm.pgs_colors,
+        "phase_ms_last_step": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "lcp_solve": tm.lcp_solve * 1e3,
+                               "pgs_sweeps": tm.pgs_kernel_time * 1e3, "post": tm.merging * 1e3, "total": tm.compute_time * 1e3},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "roofline": {"bound": "hbm", "kernel": "k_pgs_color<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": "752 B per contact per PGS iteration"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle.oracle import Oracle
+        sblob, sample = sample_workload(args.workload)
+        o = Oracle(sblob, params)
+        snb = sblob.n_bodies - 1
+        for _ in range(2):
+            o.step(0.05)
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < 15.0 and k < 50:
+            o.step(0.05)
+            k += 1
+        el = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": snb * k / el, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{sample}, {k} steps after 2 warm-up steps",
+                                "pgs_row_updates_per_s": o.row_updates() / max(o.solve_seconds(), 1e-12)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -308,6 +308,21 @@ int am3d_download_deltav(am3d_ctx* ctx, double* dv /* [n_bodies*6] */);
 int am3d_set_lambdas(am3d_ctx* ctx, const double* lambda /* [count*3] */, int count);
 /* counters: [0] kernels launched so far, [1] PGS sweep launches, [2] contact-row updates, [3] PGS kernel seconds */
 int am3d_stats(am3d_ctx* ctx, double* out4);
+/* device-side stopwatch on the context's stream: mark slot 0 (start) / 1 (stop), then read the span */
+/* merge / unmerge decisions so far: rows (step, kind, bodyLo, bodyHi); kind 0 = the pair became internal to a
+ * collection (Merging.merge, Merging.java:73-163), 1 = it left its collection (Merging.unmerge :215-374) */
+int am3d_num_events(am3d_ctx* ctx);
+int am3d_download_events(am3d_ctx* ctx, int32_t* out /* [capacity*4] */, int capacity, int* count);
+/* tests: record the Gauss-Seidel sequence of every solve; which = 0 last full solve, 1 last single sweep */
+int am3d_record_orders(am3d_ctx* ctx, int on);
+int am3d_download_order(am3d_ctx* ctx, int which, am3d_contact* out, int capacity, int* count);
+/* internal body pairs of collections (RigidCollection.bodyPairContacts with inCollection) */
+int am3d_num_internal_bpcs(am3d_ctx* ctx);
+int am3d_download_internal_bpcs(am3d_ctx* ctx, am3d_bpc* out, int capacity, int* count);
+/* one RigidCollection: x[3] R[9] v[3] omega[3] mass minv jinv[9] massAngular[9] flags alive members stamp */
+int am3d_download_collection(am3d_ctx* ctx, int slot, double* out42);
+int am3d_mark(am3d_ctx* ctx, int slot);
+int am3d_elapsed_ms(am3d_ctx* ctx, double* ms);
 /* order (position in the Gauss-Seidel sequence) the full solve gave each
  * current external contact, for replaying on the CPU oracle */
 int am3d_download_solve_order(am3d_ctx* ctx, int32_t* order, int capacity, int* count);

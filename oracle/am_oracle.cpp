@@ -1222,7 +1222,10 @@ struct System {
     for (BPC* bpc : bpcsToUnmerge) bpc->inCollection = false;
     std::set<Body*, BodyIdLess> handledBodies, subbodies, remainedBodies;
     size_t collSize = collection->bodies.size();
-    std::vector<Body*> members = collection->bodies;  // unmergeBody does not touch the list
+    // collection.bodies is in order of addition, which in the reference derives from the HashSet iteration order
+    // of merge(); canonicalised to ascending body id (unmergeBody does not touch the list)
+    std::vector<Body*> members = collection->bodies;
+    std::sort(members.begin(), members.end(), [](const Body* a, const Body* b) { return a->id < b->id; });
     for (Body* body : members) {
       if (!handledBodies.count(body)) {
         subbodies.insert(body);

@@ -58,3 +58,14 @@ def mixed_scene():
             k += 1
     sb.add_sphere(0.6, (0.1, 3.9, 0.1), v=(0, -1, 0), name="top")
     return sb.build()
+
+
+def pile_with_bullet(nx=2, ny=3, nz=2, height=45.0):
+    """a small pile that merges with the plane, and one box dropped from high above that hits it later"""
+    from adaptivemerging_b200.scene import _boxes_blob
+    base = box_stack(nx, ny, nz, pile=True)
+    xs = base.a["body_x"][1:].copy()
+    Rs = base.a["body_R"][1:].reshape(-1, 3, 3).copy()
+    xs = np.concatenate([xs, [[0.35, height, 0.25]]])
+    Rs = np.concatenate([Rs, np.eye(3)[None]])
+    return _boxes_blob(np.ones((len(xs), 3)), xs, Rs)
