@@ -893,3 +893,104 @@ def box_stack(nx, ny, nz, pile=False, pitch=1.05, gap=-1e-4, seed=12345):
         Rs[:, 2, 0] = -s
         Rs[:, 2, 2] = c
     return _boxes_blob(np.ones((n, 3)), xs, Rs)
+
+
+# ---------------------------------------------------------------------------------------------
+# blob persistence and instancing (fixtures for the GPU box, which has no reference checkout)
+# ---------------------------------------------------------------------------------------------
+def save_blob(blob: SceneBlob, path):
+    np.savez_compressed(path, __n_scenes=np.array([blob.n_scenes]), __names=np.array(blob.names, dtype=object),
+                        __overrides=np.array([repr(blob.overrides)], dtype=object),
+                        __system=np.array([int(blob.has_system_tag)]), **blob.a)
+
+
+def load_blob(path) -> SceneBlob:
+    z = np.load(path, allow_pickle=True)
+    arrays = {k: z[k] for k in z.files if not k.startswith("__")}
+    import ast
+    return SceneBlob(arrays, int(z["__n_scenes"][0]), names=list(z["__names"]),
+                     overrides=ast.literal_eval(str(z["__overrides"][0])), has_system_tag=bool(z["__system"][0]))
+
+
+def append_instances(blob: SceneBlob, body, xs, Rs, vs=None) -> SceneBlob:
+    """Append len(xs) copies of `body` (a single-shape body, e.g. a mesh sharing its sphere tree) at the given
+    poses.  Vectorised: used for the 100k sphere-tree pile of config F."""
+    n = len(xs)
+    a = blob.a
+    nb0, ns0 = blob.n_bodies, blob.n_shapes
+    assert a["body_shape_count"][body] == 1
+    sh = a["body_shape_first"][body]
+    out = {}
+    for k in _BODY_KEYS:
+        v = a[k]
+        rep = np.repeat(v[body:body + 1], n, axis=0)
+        out[k] = np.concatenate([v, rep])
+    out["body_x"][nb0:] = xs
+    out["body_R"][nb0:] = np.asarray(Rs).reshape(n, 9)
+    out["body_v"][nb0:] = 0.0 if vs is None else vs
+    out["body_omega"][nb0:] = 0.0
+    out["body_shape_first"][nb0:] = ns0 + np.arange(n, dtype=np.int32)
+    for k in _SHAPE_KEYS:
+        v = a[k]
+        out[k] = np.concatenate([v, np.repeat(v[sh:sh + 1], n, axis=0)])
+    out["shape_body"][ns0:] = nb0 + np.arange(n, dtype=np.int32)
+    for k in _NODE_KEYS + _SPRING_KEYS:
+        out[k] = a[k]
+    return SceneBlob(out, blob.n_scenes, names=[], overrides=blob.overrides, has_system_tag=blob.has_system_tag)
+
+
+def remove_bodies(blob: SceneBlob, bodies) -> SceneBlob:
+    """Drop single-shape, spring-free bodies (used to strip the template instance)."""
+    a = blob.a
+    keep = np.ones(blob.n_bodies, bool)
+    keep[list(bodies)] = False
+    keep_sh = keep[a["shape_body"]]
+    new_b = np.cumsum(keep) - 1
+    new_s = np.cumsum(keep_sh) - 1
+    out = {}
+    for k in _BODY_KEYS:
+        out[k] = a[k][keep]
+    for k in _SHAPE_KEYS:
+        out[k] = a[k][keep_sh]
+    out["body_shape_first"] = new_s[a["body_shape_first"][keep]].astype(np.int32)
+    out["shape_body"] = new_b[a["shape_body"][keep_sh]].astype(np.int32)
+    for k in _NODE_KEYS + _SPRING_KEYS:
+        out[k] = a[k]
+    if len(a["spring_type"]):
+        out["spring_body1"] = new_b[a["spring_body1"]].astype(np.int32)
+        b2 = a["spring_body2"]
+        out["spring_body2"] = np.where(b2 >= 0, new_b[np.maximum(b2, 0)], b2).astype(np.int32)
+    names = [n for n, k in zip(blob.names, keep) if k] if blob.names else []
+    return SceneBlob(out, blob.n_scenes, names=names, overrides=blob.overrides, has_system_tag=blob.has_system_tag)
+
+
+def random_rotations(n, seed=12345):
+    """uniformly random unit axis, angle U(0, 2 pi), PCG32 stream"""
+    u = PCG32(seed).uniform(4 * n).reshape(n, 4)
+    z = 2 * u[:, 0] - 1
+    ph = 2 * np.pi * u[:, 1]
+    s = np.sqrt(np.maximum(0.0, 1 - z * z))
+    ax = np.stack([s * np.cos(ph), s * np.sin(ph), z], 1)
+    ang = 2 * np.pi * u[:, 2]
+    c, sn = np.cos(ang), np.sin(ang)
+    t = 1 - c
+    x, y, zz = ax[:, 0], ax[:, 1], ax[:, 2]
+    R = np.empty((n, 3, 3))
+    R[:, 0, 0] = t * x * x + c; R[:, 0, 1] = t * x * y - sn * zz; R[:, 0, 2] = t * x * zz + sn * y
+    R[:, 1, 0] = t * x * y + sn * zz; R[:, 1, 1] = t * y * y + c; R[:, 1, 2] = t * y * zz - sn * x
+    R[:, 2, 0] = t * x * zz - sn * y; R[:, 2, 1] = t * y * zz + sn * x; R[:, 2, 2] = t * zz * zz + c
+    return R
+
+
+def funnel_pile(template: SceneBlob, nx=100, ny=10, nz=100, pitch=0.95, y0=110.0, seed=12345):
+    """Config F: funnel.xml without box1..3 plus nx*ny*nz instances of the torso_flux sphere-tree mesh on a lattice
+    centred on x = z = 0 starting at y0.  `template` = the funnel scene with ONE mesh body as its LAST body."""
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    n = ix.size
+    xs = np.empty((n, 3))
+    xs[:, 0] = (ix.ravel() - (nx - 1) / 2.0) * pitch
+    xs[:, 1] = y0 + iy.ravel() * pitch
+    xs[:, 2] = (iz.ravel() - (nz - 1) / 2.0) * pitch
+    tb = template.n_bodies - 1
+    blob = append_instances(template, tb, xs, random_rotations(n, seed))
+    return remove_bodies(blob, [tb])

@@ -1444,11 +1444,13 @@ struct System {
   // solveLCP :108-137
   void solveLCP(double dt) {
     if (!contacts.empty()) {
+      // the externally supplied sequence only orders the Gauss-Seidel sweeps; `contacts` itself keeps the
+      // reference's emission order (it decides which duplicate-key contact the warm-start map retains, :443-448)
       std::vector<Contact*> list = contacts;
-      if (haveOrderFull) { applyOrder(list, orderFull); contacts = list; }
-      updateJacobiansThatNeedUpdating(contacts, false);
+      if (haveOrderFull) applyOrder(list, orderFull);
+      updateJacobiansThatNeedUpdating(list, false);
       double t0 = nowSec();
-      pgsSolve(contacts, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
+      pgsSolve(list, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
       T.lcp_solve = nowSec() - t0;
       T.pgs_iterations = lastIterations;
       rowUpdates += 3L * (long)contacts.size() * lastIterations;
