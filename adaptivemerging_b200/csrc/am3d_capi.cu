@@ -204,6 +204,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
   c->T.unmerging_build = c->T.unmerging;
   c->T.compute_time = evMs(c, 0, 7) * 1e-3;
   c->T.n_bodies = NB;
+  c->T.n_contacts = c->cur.n;  // collision.contacts.size() at the end of the step, unmerge-appended contacts included
   c->T.n_collections = c->nCollections;
 }
 
@@ -271,6 +272,12 @@ int am3d_create(int device, am3d_ctx** out) {
     for (int i = 0; i < 16; i++) CK(cudaEventCreate(&c->ev[i]));
     c->evCreated = true;
     am3d_default_params(&c->P);
+    int coop = 0, sms = 0, perSm = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent, 128, 0));
+    c->coopBlocks = coop ? sms * perSm : 0;
+    if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
     delete c;
     return e.code;

@@ -40,7 +40,7 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
   void ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
-    size_t ncap = n + n / 4 + 64;
+    size_t ncap = n + n / 2 + 256;  // regrowth costs a cudaMalloc + cudaFree (device-wide syncs): grow geometrically
     T* q = nullptr;
     CK(cudaMalloc(&q, ncap * sizeof(T)));
     if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
@@ -183,6 +183,8 @@ struct am3d_ctx {
   ContactSet icon, icon2;   // internal contacts of collections (RigidCollection.internalContacts), grouped by pair
   BpcSet ibp, ibp2;         // internal body pairs (BodyPairContact.inCollection == true)
   DevBuf<int> ibpCut, ibpCut2;
+  DevBuf<unsigned long long> tailKey, tailKeySorted;
+  DevBuf<int> tailVal, tailIdx;
   DevBuf<double> B2CR, B2Ct;  // RigidBody.transformB2C of the leaves
   DevBuf<int> collCount, collStart, members, memVal, changedList, collMode, collFlagAcc, freeList;
   DevBuf<unsigned int> memKey, memKeySorted;
@@ -216,6 +218,8 @@ struct am3d_ctx {
   am3d_timings T;
   cudaEvent_t ev[16];
   bool evCreated = false;
+  int coopBlocks = 0;     // co-resident CTAs for the cooperative PGS kernel (0: cooperative launch unsupported)
+  int usePersistent = 1;  // 0 never, 1 heuristic, 2 always (AM3D_PGS_PERSISTENT)
   long long solveLaunches = 0;
   long long kernelLaunches = 0;
   double rowUpdates = 0, solveSeconds = 0;

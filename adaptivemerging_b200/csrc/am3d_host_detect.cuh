@@ -102,9 +102,17 @@ static void buildBodyPairs(am3d_ctx* c) {
 static void warmStart(am3d_ctx* c) {
   int nbp = c->bp.n;
   if (nbp == 0) return;
+  int nt = c->prev.n - c->prev.nSorted;
+  if (nt > 0) {  // index the out-of-order tail of last step's contact list (appended by an unmerge)
+    c->tailKey.ensure(nt + 1); c->tailKeySorted.ensure(nt + 1); c->tailVal.ensure(nt + 1); c->tailIdx.ensure(nt + 1);
+    LAUNCH(c, k_tail_keys, nblk(nt), BLK, nt, c->prev.nSorted, c->prev.key0.p, c->tailKey.p, c->tailVal.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->tailKey.p, c->tailKeySorted.p, c->tailVal.p, c->tailIdx.p, nt, 0, 64, c->stream);
+    });
+  }
   WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,
             c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
-            c->prev.n, c->prev.nSorted, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, c->prev.viol.p, c->prev.lam.p,
+            c->prev.n, c->prev.nSorted, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, c->prev.viol.p, c->prev.lam.p,
             c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
   LAUNCH(c, k_warm_start, nblk(nbp, 128), 128, nbp, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p, W);
 }

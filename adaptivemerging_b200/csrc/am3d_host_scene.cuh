@@ -155,7 +155,22 @@ static void resetState(am3d_ctx* c) {
   c->counters.ensure(64); c->counters.zero(64, c->stream);
   c->iterState.ensure(8); c->iterState.zero(8, c->stream);
   c->cur.n = 0; c->prev.n = 0; c->bp.n = 0; c->bpPrev.n = 0; c->cur.nSorted = 0; c->prev.nSorted = 0;
-  c->cur.ensure(1024); c->prev.ensure(1024); c->bp.ensure(256); c->bpPrev.ensure(256);
+  {
+    // reserve for ~8 contacts and ~4 body pairs per body up front so that steady growth of the contact count (a pile
+    // settling layer by layer) does not reallocate every few steps
+    size_t rc = (size_t)NB * 8 + 4096, rb = (size_t)NB * 4 + 1024;
+    c->cur.ensure(rc); c->prev.ensure(rc); c->bp.ensure(rb); c->bpPrev.ensure(rb);
+    c->hitPos.ensure(3 * rc * 2); c->hitNrm.ensure(3 * rc * 2); c->hitViol.ensure(rc * 2); c->hitMeta.ensure(4 * rc * 2);
+    c->scD.ensure(9 * rc); c->scR.ensure(6 * rc); c->scB.ensure(3 * rc); c->scDiag.ensure(3 * rc); c->scLam.ensure(3 * rc);
+    c->scSrc.ensure(rc); c->scState.ensure(rc);
+    c->sgB1.ensure(rb); c->sgB2.ensure(rb); c->sgStart.ensure(rb + 2); c->sgCount.ensure(rb + 2); c->sgFlags.ensure(rb);
+    c->sgBpc.ensure(rb); c->sgMass.ensure(20 * rb); c->sgMu.ensure(rb);
+    c->tmpI0.ensure(rc); c->tmpI1.ensure(rc); c->tmpI2.ensure(rb); c->tmpI3.ensure(rb);
+    if (c->P.enable_merging) {  // internal tables of the collections (and their compaction targets)
+      c->icon.ensure(rc / 2); c->icon2.ensure(rc / 2); c->ibp.ensure(rb / 2); c->ibp2.ensure(rb / 2);
+      c->ibpCut.ensure(rb / 2); c->ibpCut2.ensure(rb / 2);
+    }
+  }
   c->totalSteps = 0;
   c->mergingEvent = false;
   c->nCollections = 0;

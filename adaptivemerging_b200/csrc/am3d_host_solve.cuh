@@ -119,18 +119,35 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold};
   int iterations = sweep ? P.iterations_in_collection : P.iterations;
   CK(cudaEventRecord(c->ev[sweep ? 8 : 10], c->stream));
-  for (int k = 0; k < c->nColors; k++) {
-    int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-    LAUNCH(c, k_pgs_color<0>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
-  }
-  for (int it = 0; it < iterations; it++) {
-    int last = it == iterations - 1;
+  // many small colours (hubs, batched scenes): one cooperative launch with grid barriers; few large colours: one
+  // launch per colour (no barrier cost, full occupancy per launch)
+  long long avgGroups = ng / std::max(1, c->nColors);
+  bool persistent = c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
+  if (persistent) {
+    c->dColorStart.ensure(c->colorStart.size() + 1);
+    CK(cudaMemcpyAsync(c->dColorStart.p, c->colorStart.data(), c->colorStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    int nColors = c->nColors, chk = sweep ? 0 : 1;
+    const int* dcs = c->dColorStart.p;
+    double* dvp = c->dv.p;
+    unsigned long long* isp = c->iterState.p;
+    void* args[] = {&nColors, &dcs, &S, &dvp, &PP, &iterations, &chk, &isp};
+    CK(cudaLaunchCooperativeKernel((void*)k_pgs_persistent, dim3(c->coopBlocks), dim3(128), args, 0, c->stream));
+    c->kernelLaunches++;
+    c->solveLaunches++;
+  } else {
     for (int k = 0; k < c->nColors; k++) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-      LAUNCH(c, k_pgs_color<1>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
-      c->solveLaunches++;
+      LAUNCH(c, k_pgs_color<0>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
     }
-    LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);
+    for (int it = 0; it < iterations; it++) {
+      int last = it == iterations - 1;
+      for (int k = 0; k < c->nColors; k++) {
+        int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
+        LAUNCH(c, k_pgs_color<1>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        c->solveLaunches++;
+      }
+      LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);
+    }
   }
   CK(cudaEventRecord(c->ev[sweep ? 9 : 11], c->stream));
   if (!sweep) CK(cudaMemsetAsync(c->bp.nActive.p, 0, (nExt + 1) * sizeof(int), c->stream));

@@ -6,7 +6,10 @@
 //   (MotionMetricProcessor.java:39-73, BodyPairContact.java:83-121).
 #pragma once
 #include "am3d_ctx.h"
+#include <cooperative_groups.h>
+
 #include "am3d_math.cuh"
+namespace cg = cooperative_groups;
 
 #define BLK 256
 static inline int nblk(long long n, int b = BLK) { return (int)((n + b - 1) / b); }
@@ -194,6 +197,8 @@ struct WarmCtx {
   int* isNew;
   // previous (entries [0,npSorted) are in canonical key order, [npSorted,np) were appended by an unmerge)
   int np, npSorted;
+  const unsigned long long* tailKey;  // key0 of the appended entries, sorted
+  const int* tailIdx;                 // their positions in the previous contact arrays
   const unsigned long long *pkey0, *pkey1;
   const int *pb1, *pleaf;
   const double *ppB1, *pviol;
@@ -215,8 +220,14 @@ __device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsi
       if (best < 0 || rk > bestRank) { best = j; bestRank = rk; }
     }
   }
-  for (int j = W.npSorted; j < W.np; j++) {  // appended later in the list: they win over earlier duplicates
-    if (W.pkey0[j] == k0 && W.pkey1[j] == k1) { best = j; bestRank = 0x7fffffff; }
+  int nt = W.np - W.npSorted;
+  if (nt > 0) {  // entries appended later in the list (by an unmerge) win over earlier duplicates
+    int tl = 0, th = nt;
+    while (tl < th) { int mid = (tl + th) >> 1; if (W.tailKey[mid] < k0) tl = mid + 1; else th = mid; }
+    for (int t = tl; t < nt && W.tailKey[t] == k0; t++) {
+      int j = W.tailIdx[t];
+      if (W.pkey1[j] == k1) { best = j; bestRank = 0x7fffffff; }
+    }
   }
   return best;
 }
@@ -657,7 +668,84 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
   dvp[5] = lambda * tz + dvp[5];
 }
 
+// One body-pair group: its contacts in sequence, the deltaV of its two solver bodies held in registers.
 // MODE 0: confidentWarmStart (PGS.java:250-256); MODE 1: one Gauss-Seidel sweep (:105-181)
+template <int MODE>
+__device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
+                                         double& localMax) {
+  int a = S.sgB1[p], b = S.sgB2[p];
+  int start = S.sgStart[p], cnt = S.sgCount[p];
+  double M[20];
+  const double* Mp = S.sgMass + 20 * p;
+#pragma unroll
+  for (int k = 0; k < 20; k++) M[k] = Mp[k];
+  double mu = S.sgMu[p];
+  bool clamp = S.sgFlags[p] & 1;
+  double dv1[6], dv2[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { dv1[k] = a >= 0 ? __ldcg(dv + 6 * a + k) : 0.0; dv2[k] = b >= 0 ? __ldcg(dv + 6 * b + k) : 0.0; }
+  for (int c = 0; c < cnt; c++) {
+    int idx = start + c;
+    const double* Dp = S.scD + 9 * idx;
+    d3 dir[3] = {ld3(Dp), ld3(Dp + 3), ld3(Dp + 6)};
+    d3 r1 = ld3(S.scR + 6 * idx), r2 = ld3(S.scR + 6 * idx + 3);
+    double lam[3] = {S.scLam[3 * idx], S.scLam[3 * idx + 1], S.scLam[3 * idx + 2]};
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+        if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, lam[k]);
+        if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, lam[k]);
+      }
+    } else {
+      double bb[3] = {S.scB[3 * idx], S.scB[3 * idx + 1], S.scB[3 * idx + 2]};
+      double DD[3] = {S.scDiag[3 * idx], S.scDiag[3 * idx + 1], S.scDiag[3 * idx + 2]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+        double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
+        double prev = lam[k];
+        double l = (DD[k] * prev - P.omega * (bb[k] + Jdv)) / (DD[k] + P.compliance);
+        if (clamp) {
+          if (k == 0) l = fmax(0.0, l);
+          else {
+            double limit = mu * lam[0];
+            l = fmax(l, -limit);
+            l = fmin(l, limit);
+          }
+        }
+        lam[k] = l;
+        double diff = l - prev;
+        if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
+        if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
+        localMax = fmax(localMax, fabs(diff));
+      }
+      S.scLam[3 * idx] = lam[0]; S.scLam[3 * idx + 1] = lam[1]; S.scLam[3 * idx + 2] = lam[2];
+      if (lastIter) {
+        // Contact.updateContactState :385-398
+        d3 jaw1 = vcross(dir[1], r1), jbw1 = vcross(r2, dir[1]);
+        d3 jaw2 = vcross(dir[2], r1), jbw2 = vcross(r2, dir[2]);
+        double w1 = bb[1] + (dot6(vscale(-1, dir[1]), jaw1, dv1) + dot6(dir[1], jbw1, dv2));
+        double w2 = bb[2] + (dot6(vscale(-1, dir[2]), jaw2, dv1) + dot6(dir[2], jbw2, dv2));
+        int st;
+        if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
+        else if (fabs(w1) > P.sliding) st = AM3D_CS_ONEDGE;
+        else if (fabs(w2) > P.sliding) st = AM3D_CS_ONEDGE;
+        else st = AM3D_CS_CLEAR;
+        S.scState[idx] = st;
+      }
+    }
+  }
+  if (a >= 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+  }
+  if (b >= 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
@@ -665,83 +753,48 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
   if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
   int p = gBegin + blockIdx.x * blockDim.x + threadIdx.x;
   double localMax = 0;
-  if (p < gEnd) {
-    int a = S.sgB1[p], b = S.sgB2[p];
-    int start = S.sgStart[p], cnt = S.sgCount[p];
-    double M[20];
-    const double* Mp = S.sgMass + 20 * p;
-#pragma unroll
-    for (int k = 0; k < 20; k++) M[k] = Mp[k];
-    double mu = S.sgMu[p];
-    bool clamp = S.sgFlags[p] & 1;
-    double dv1[6], dv2[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) { dv1[k] = a >= 0 ? dv[6 * a + k] : 0.0; dv2[k] = b >= 0 ? dv[6 * b + k] : 0.0; }
-    for (int c = 0; c < cnt; c++) {
-      int idx = start + c;
-      const double* Dp = S.scD + 9 * idx;
-      d3 dir[3] = {ld3(Dp), ld3(Dp + 3), ld3(Dp + 6)};
-      d3 r1 = ld3(S.scR + 6 * idx), r2 = ld3(S.scR + 6 * idx + 3);
-      double lam[3] = {S.scLam[3 * idx], S.scLam[3 * idx + 1], S.scLam[3 * idx + 2]};
-      if (MODE == 0) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
-          if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, lam[k]);
-          if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, lam[k]);
-        }
-      } else {
-        double bb[3] = {S.scB[3 * idx], S.scB[3 * idx + 1], S.scB[3 * idx + 2]};
-        double DD[3] = {S.scDiag[3 * idx], S.scDiag[3 * idx + 1], S.scDiag[3 * idx + 2]};
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
-          double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
-          double prev = lam[k];
-          double l = (DD[k] * prev - P.omega * (bb[k] + Jdv)) / (DD[k] + P.compliance);
-          if (clamp) {
-            if (k == 0) l = fmax(0.0, l);
-            else {
-              double limit = mu * lam[0];
-              l = fmax(l, -limit);
-              l = fmin(l, limit);
-            }
-          }
-          lam[k] = l;
-          double diff = l - prev;
-          if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
-          if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
-          localMax = fmax(localMax, fabs(diff));
-        }
-        S.scLam[3 * idx] = lam[0]; S.scLam[3 * idx + 1] = lam[1]; S.scLam[3 * idx + 2] = lam[2];
-        if (lastIter) {
-          // Contact.updateContactState :385-398
-          d3 jaw1 = vcross(dir[1], r1), jbw1 = vcross(r2, dir[1]);
-          d3 jaw2 = vcross(dir[2], r1), jbw2 = vcross(r2, dir[2]);
-          double w1 = bb[1] + (dot6(vscale(-1, dir[1]), jaw1, dv1) + dot6(dir[1], jbw1, dv2));
-          double w2 = bb[2] + (dot6(vscale(-1, dir[2]), jaw2, dv1) + dot6(dir[2], jbw2, dv2));
-          int st;
-          if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
-          else if (fabs(w1) > P.sliding) st = AM3D_CS_ONEDGE;
-          else if (fabs(w2) > P.sliding) st = AM3D_CS_ONEDGE;
-          else st = AM3D_CS_CLEAR;
-          S.scState[idx] = st;
-        }
-      }
-    }
-    if (a >= 0) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
-    }
-    if (b >= 0) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
-    }
-  }
+  if (p < gEnd) pgsGroup<MODE>(p, S, dv, P, lastIter, localMax);
   if (MODE == 1) {
     // max |delta lambda| of the sweep (PGS.java:125,159,176): non-negative doubles order like their bit patterns
     for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
     if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
+  }
+}
+
+// The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
+// colour.  Used when the colours are many and small (merged collections are hubs of the contact graph, batched
+// scenes): thousands of tiny launches become grid syncs.  Same Gauss-Seidel sequence as the per-colour launches.
+__global__ void __launch_bounds__(128)
+k_pgs_persistent(int nColors, const int* __restrict__ colorStart, SolveArrays S, double* __restrict__ dv, PgsParams P,
+                 int iterations, int checkTolerance, unsigned long long* __restrict__ iterState) {
+  cg::grid_group grid = cg::this_grid();
+  int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  double dummy = 0;
+  for (int c = 0; c < nColors; c++) {
+    int g1 = colorStart[c + 1];
+    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0>(p, S, dv, P, 0, dummy);
+    grid.sync();
+  }
+  for (int it = 0; it < iterations; it++) {
+    int last = it == iterations - 1;
+    double localMax = 0;
+    for (int c = 0; c < nColors; c++) {
+      int g1 = colorStart[c + 1];
+      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1>(p, S, dv, P, last, localMax);
+      grid.sync();
+    }
+    for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+    if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
+    grid.sync();
+    if (tid == 0) {
+      iterState[2] += 1;
+      double m = __longlong_as_double((long long)iterState[0]);
+      if (checkTolerance && m < P.tolerance) iterState[1] = 1;
+      iterState[3] = iterState[0];
+      iterState[0] = 0;
+    }
+    grid.sync();
+    if (((volatile unsigned long long*)iterState)[1]) break;
   }
 }
 __global__ void k_iter_end(unsigned long long* iterState, double tolerance, int checkTolerance) {
@@ -934,4 +987,12 @@ __global__ void k_has_ext(int nbp, const int* __restrict__ alive, const int* __r
   if ((flags[l1] & AM3D_F_PINNED) || (flags[l2] & AM3D_F_PINNED)) return;
   int a = parent[l1] >= 0 ? parent[l1] : l1, c = parent[l2] >= 0 ? parent[l2] : l2;
   hasExt[l1] = 1; hasExt[l2] = 1; hasExt[a] = 1; hasExt[c] = 1;
+}
+
+__global__ void k_tail_keys(int nt, int base, const unsigned long long* __restrict__ key0, unsigned long long* __restrict__ k,
+                            int* __restrict__ v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  k[i] = key0[base + i];
+  v[i] = base + i;
 }

@@ -35,25 +35,46 @@ METRIC = "body_steps_per_s"
 UNIT = "body-steps/s"
 
 
-def build_workload(name, size):
-    """Returns (blob, params, description).  Sizes are per GPU."""
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def build_workload(name, size, merging):
+    """Returns (blob, params, description).  Sizes are per GPU (weak scaling)."""
     from adaptivemerging_b200.ctypes_defs import apply_overrides, default_params
-    from adaptivemerging_b200.scene import box_stack
+    from adaptivemerging_b200.scene import box_stack, funnel_pile, load_blob
     p = default_params()
+    p.enable_merging = int(merging)
+    if name == "batch":
+        copies = size or 512
+        one = load_blob(os.path.join(GOLDEN, "scene_tower25platform.npz"))
+        p = apply_overrides(p, one.overrides)
+        blob = one.replicate(copies)
+        return blob, p, (f"{copies} independent copies of scenes3D/tower25platform.xml per GPU (config B of BASELINE.json: "
+                         f"4096 copies over 8 GPUs), merging {'on' if merging else 'off'}")
     if name in ("stack", "pile"):
         n = size or 100
-        ny = n
-        blob = box_stack(n, ny, n, pile=(name == "pile"))
-        p.enable_merging = 0  # TODO(merging on GPU): config M is quoted with merging on and off
-        return blob, p, f"{name} {n}x{ny}x{n} unit boxes on a plane (config M of BASELINE.json), merging off"
+        blob = box_stack(n, n, n, pile=(name == "pile"))
+        return blob, p, f"{name} {n}x{n}x{n} unit boxes on a plane (config M of BASELINE.json), merging {'on' if merging else 'off'}"
+    if name == "funnel":
+        n = size or 100
+        tmpl = load_blob(os.path.join(GOLDEN, "scene_funnel_template.npz"))
+        p = apply_overrides(p, tmpl.overrides)
+        blob = funnel_pile(tmpl, nx=n, ny=10, nz=n)
+        return blob, p, (f"funnel.xml + {n}x10x{n} torso_flux sphere-tree bodies (config F of BASELINE.json), "
+                         f"merging {'on' if merging else 'off'}")
     raise SystemExit(f"unknown workload {name}")
 
 
 def sample_workload(name):
     """Bounded CPU sample of the same workload (the reference's broadphase is O(N^2))."""
-    from adaptivemerging_b200.scene import box_stack
+    from adaptivemerging_b200.scene import box_stack, funnel_pile, load_blob
+    if name == "batch":
+        return load_blob(os.path.join(GOLDEN, "scene_tower25platform.npz")), "1 copy of tower25platform.xml (328 bodies)"
     if name in ("stack", "pile"):
         return box_stack(12, 100, 12, pile=(name == "pile")), "12x100x12 = 14,400 boxes of the same stack"
+    if name == "funnel":
+        tmpl = load_blob(os.path.join(GOLDEN, "scene_funnel_template.npz"))
+        return funnel_pile(tmpl, nx=10, ny=10, nz=10), "funnel + 10x10x10 = 1,000 torso bodies"
     raise SystemExit(name)
 
 
@@ -123,11 +144,14 @@ def run_reference(args, rank, world):
         return
     from adaptivemerging_b200.ctypes_defs import default_params
     from oracle.oracle import Oracle
+    from adaptivemerging_b200.ctypes_defs import apply_overrides
     blob, sample = sample_workload(args.workload)
-    p = default_params()
-    p.enable_merging = 0
+    p = apply_overrides(default_params(), blob.overrides)
+    p.enable_merging = int(args.merging)
     o = Oracle(blob, p)
-    nb = blob.n_bodies - 1
+    for _ in range(args.settle):
+        o.step(0.05)
+    nb = int((blob.a["body_type"] != 1).sum())
     for _ in range(args.warmup):
         o.step(0.05)
     t0 = time.perf_counter()
@@ -138,7 +162,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "sample": sample, "dt": 0.05},
+            "config": {"workload": args.workload, "sample": sample, "dt": 0.05, "merging": bool(args.merging),
+                       "settle_steps": args.settle},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "pgs_row_updates_per_s": o.row_updates() / max(o.solve_seconds(), 1e-12)}
@@ -151,9 +176,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default="stack")
+    ap.add_argument("--workload", default="batch", choices=["batch", "stack", "pile", "funnel"])
+    ap.add_argument("--merging", type=int, default=1)
     ap.add_argument("--size", type=int, default=0)
-    ap.add_argument("--settle", type=int, default=20, help="untimed steps before the warm-up so that contacts exist")
+    ap.add_argument("--settle", type=int, default=40, help="untimed steps before the warm-up so that contacts exist")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -176,7 +202,7 @@ def main():
         raise SystemExit("no CUDA device: the rigid-body step has no CPU fallback")
 
     from adaptivemerging_b200.system import RigidBodySystem
-    blob, params, desc = build_workload(args.workload, args.size)
+    blob, params, desc = build_workload(args.workload, args.size, args.merging)
     nb = int((blob.a["body_type"] != 1).sum())  # non-plane leaf bodies
     sysm = RigidBodySystem(local).load(blob, params)
 
@@ -255,7 +281,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "bodies_per_gpu": nb, "dt": 0.05,
+        "config": {"workload": args.workload, "description": desc, "bodies_per_gpu": nb, "dt": 0.05, "merging": bool(args.merging),
                    "pgs_iterations": params.iterations, "settle_steps": args.settle,
                    "l2": "working set (body + contact arrays) exceeds the 126 MB L2" if nb >= 200000 else
                          "working set fits L2; no flush between steps (steps are data dependent)"},
@@ -264,7 +290,7 @@ def main():
         "gpu_launches": int(float(tot[3])),
         "clocks": clk,
         "pgs_row_updates_per_s": float(tot[1]) / max(solve_s, 1e-12) if world == 1 else float(tot[1]) / max(solve_s, 1e-12),
-        "contacts_last_step": tm.n_contacts, "pairs_last_step": tm.n_pairs, "pgs_colors": tm.pgs_colors,
+        "collections_last_step": tm.n_collections, "contacts_last_step": tm.n_contacts, "pairs_last_step": tm.n_pairs, "pgs_colors": tm.pgs_colors,
         "phase_ms_last_step": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "lcp_solve": tm.lcp_solve * 1e3,
                                "pgs_sweeps": tm.pgs_kernel_time * 1e3, "post": tm.merging * 1e3, "total": tm.compute_time * 1e3},
         "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -276,8 +302,8 @@ def main():
         from oracle.oracle import Oracle
         sblob, sample = sample_workload(args.workload)
         o = Oracle(sblob, params)
-        snb = sblob.n_bodies - 1
-        for _ in range(2):
+        snb = int((sblob.a["body_type"] != 1).sum())
+        for _ in range(args.settle):
             o.step(0.05)
         t0 = time.perf_counter()
         k = 0
@@ -286,7 +312,7 @@ def main():
             k += 1
         el = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": snb * k / el, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{sample}, {k} steps after 2 warm-up steps",
+                                "sample": f"{sample}, {k} steps after {args.settle} settle steps",
                                 "pgs_row_updates_per_s": o.row_updates() / max(o.solve_seconds(), 1e-12)}
     print(json.dumps(line), flush=True)
     if dist is not None:
