@@ -18,7 +18,7 @@ EXPORTS = [
     "am3d_get_timings", "am3d_total_steps", "am3d_detect", "am3d_upload_contacts", "am3d_solve",
     "am3d_download_deltav", "am3d_set_lambdas", "am3d_stats", "am3d_download_solve_order", "am3d_mark", "am3d_elapsed_ms",
     "am3d_num_events", "am3d_download_events", "am3d_record_orders", "am3d_download_order", "am3d_num_internal_bpcs",
-    "am3d_download_internal_bpcs", "am3d_download_collection",
+    "am3d_download_internal_bpcs", "am3d_download_collection", "am3d_set_option", "am3d_add_velocities",
 ]
 
 _LIB = None
@@ -47,6 +47,7 @@ def load():
         L.am3d_solve.argtypes = [C.c_void_p, C.c_double]
         L.am3d_mark.argtypes = [C.c_void_p, C.c_int]
         L.am3d_record_orders.argtypes = [C.c_void_p, C.c_int]
+        L.am3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.am3d_download_collection.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.am3d_num_contacts.argtypes = [C.c_void_p, C.c_int]
         for n in ["am3d_destroy", "am3d_sync", "am3d_reset", "am3d_num_bodies", "am3d_num_bpcs", "am3d_total_steps",

@@ -60,6 +60,7 @@ static void fetchContacts(am3d_ctx* c, ContactSet& S, int n, am3d_contact* out, 
     o.bv1 = bv1[i]; o.bv2 = bv2[i]; o.info = info[i]; o.leaf = leaf[i]; o.state = state[i]; o.new_this_step = isNew[i];
     o.color = (!gcol.empty() && bpc[i] >= 0 && bpc[i] < ng) ? gcol[bpc[i]] : -1;
     o.in_collection = internal;
+    o.hub_mask = 0; o._pad = 0;
     for (int k = 0; k < 3; k++) {
       o.contactB1[k] = pB1[3 * i + k]; o.normalB1[k] = nB1[3 * i + k]; o.tangent1B1[k] = t1B1[3 * i + k]; o.tangent2B1[k] = t2B1[3 * i + k];
       o.point_w[k] = pW[3 * i + k]; o.normal_w[k] = nW[3 * i + k]; o.lambda[k] = lam[3 * i + k]; o.lambda_warm[k] = lamW[3 * i + k];
@@ -79,10 +80,26 @@ static void snapshotOrder(am3d_ctx* c, int which) {
   std::vector<am3d_contact> ext(c->cur.n), in(which ? c->icon.n : 0);
   fetchContacts(c, c->cur, c->cur.n, ext.data(), 0);
   if (which) fetchContacts(c, c->icon, c->icon.n, in.data(), 1);
+  // per solve position: dense colour index and hub sides of the group the contact belongs to
+  int ng = c->nGroups;
+  std::vector<int> sgStart(ng), sgCount(ng), sgFlags(ng), sgBpc(ng), gcol(ng);
+  CK(cudaMemcpy(sgStart.data(), c->sgStart.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sgCount.data(), c->sgCount.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sgFlags.data(), c->sgFlags.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sgBpc.data(), c->sgBpc.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(gcol.data(), c->grpColor.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<int> posColor(n, 0), posHub(n, 0);
+  for (int p = 0; p < ng; p++)
+    for (int k = 0; k < sgCount[p]; k++) {
+      int idx = sgStart[p] + k;
+      if (idx < n) { posColor[idx] = c->colorDense[gcol[sgBpc[p]]]; posHub[idx] = ((sgFlags[p] & SG_HUB1) ? 1 : 0) | ((sgFlags[p] & SG_HUB2) ? 2 : 0); }
+    }
   dst.resize(n);
   for (int k = 0; k < n; k++) {
     int set = ord[k] >> 30, i = ord[k] & 0x3fffffff;
     dst[k] = set ? in[i] : ext[i];
+    dst[k].color = posColor[k];
+    dst[k].hub_mask = posHub[k];
   }
 }
 
@@ -406,6 +423,17 @@ int am3d_add_body_velocity(am3d_ctx* c, int body, const double dv[3], const doub
   API_END(c)
 }
 
+int am3d_add_velocities(am3d_ctx* c, const double* dv, const double* domega) {
+  API_BEGIN(c)
+  if (!c->haveScene || !dv || !domega) throw AmError(AM3D_EINVAL, "no scene / null buffers");
+  int nb = c->NB;
+  c->pokeV.ensure(3 * (size_t)nb); c->pokeW.ensure(3 * (size_t)nb);
+  CK(cudaMemcpyAsync(c->pokeV.p, dv, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->pokeW.p, domega, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_add_velocities, nblk(nb), BLK, nb, c->parent.p, c->pokeV.p, c->pokeW.p, c->v.p, c->w.p);
+  API_END(c)
+}
+
 int am3d_num_contacts(am3d_ctx* c, int include_internal) {
   if (!c) return AM3D_EINVAL;
   return c->cur.n + (include_internal ? c->icon.n : 0);
@@ -517,6 +545,8 @@ int am3d_solve(am3d_ctx* c, double dt) {
   if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
   applyExternalForces(c);  // clear + gravity + springs, deltaV = 0
   runSolve(c, dt, false);
+  c->orderFullKeys.clear();
+  if (c->recordOrders) snapshotOrder(c, 0);
   API_END(c)
 }
 
@@ -553,6 +583,15 @@ int am3d_stats(am3d_ctx* c, double* out /* [4]: kernel launches, solve launches,
   if (!c || !out) return AM3D_EINVAL;
   out[0] = (double)c->kernelLaunches; out[1] = (double)c->solveLaunches; out[2] = c->rowUpdates; out[3] = c->solveSeconds;
   return AM3D_OK;
+}
+
+int am3d_set_option(am3d_ctx* c, const char* name, double value) {
+  API_BEGIN(c)
+  if (!name) throw AmError(AM3D_EINVAL, "null option name");
+  if (!strcmp(name, "hub_min_degree")) c->hubMin = (int)value;
+  else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
+  else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);
+  API_END(c)
 }
 
 // device-side timer on the context's own stream: am3d_mark(slot 0/1) + am3d_elapsed_ms
@@ -602,8 +641,7 @@ int am3d_debug_solve_row(am3d_ctx* c, int contact, double* out /* [50] */) {
   for (int k = 0; k < n; k++) if (src[k] == contact) idx = k;
   if (idx < 0) throw AmError(AM3D_EINVAL, "contact not in the last solve");
   auto g = [&](double* d, const double* p, int m) { CK(cudaMemcpy(d, p, m * sizeof(double), cudaMemcpyDeviceToHost)); };
-  g(out, c->scD.p + 9 * idx, 9); g(out + 9, c->scR.p + 6 * idx, 6); g(out + 15, c->scB.p + 3 * idx, 3);
-  g(out + 18, c->scDiag.p + 3 * idx, 3); g(out + 21, c->scLam.p + 3 * idx, 3);
+  g(out, c->scP.p + 24 * (size_t)idx, 24);
   int bpc;
   CK(cudaMemcpy(&bpc, c->cur.bpc.p + contact, sizeof(int), cudaMemcpyDeviceToHost));
   int pos, col, b1, b2, st, cnt;

@@ -183,6 +183,7 @@ struct am3d_ctx {
   ContactSet icon, icon2;   // internal contacts of collections (RigidCollection.internalContacts), grouped by pair
   BpcSet ibp, ibp2;         // internal body pairs (BodyPairContact.inCollection == true)
   DevBuf<int> ibpCut, ibpCut2;
+  DevBuf<double> pokeV, pokeW;
   DevBuf<unsigned long long> tailKey, tailKeySorted;
   DevBuf<int> tailVal, tailIdx;
   DevBuf<double> B2CR, B2Ct;  // RigidBody.transformB2C of the leaves
@@ -206,7 +207,13 @@ struct am3d_ctx {
   DevBuf<int> sgB1, sgB2, sgStart, sgCount, sgFlags, sgBpc;  // per solve group (colour-major)
   DevBuf<double> sgMass;                            // [20] minv1,jinv1,minv2,jinv2
   DevBuf<double> sgMu;
-  DevBuf<double> scD, scR, scB, scDiag, scLam;      // per contact in solve order: dirs[9], r1r2[6], b[3], D[3], lam[3]
+  DevBuf<double> scP;                               // per contact in solve order: [24] n t1 t2 | r1 r2 | b | D | lambda
+  DevBuf<double> hubDelta;                          // [12] per group
+  DevBuf<int> grpDegree, grpHubMask, hubN, hubScan, hubSlot, hubSlotSorted, hubHead, hubRunStart, hubRunBody, hubRunColor, dColorRunStart;
+  DevBuf<unsigned long long> hubKey, hubKeySorted;
+  std::vector<int> colorRunStart, colorDense;       // host: first hub run of each (dense) colour; raw colour -> dense index
+  int nHubRuns = 0, nHubEntries = 0;
+  int hubMin = 64;                                  // degree (in body pairs) from which a body is treated as a hub; 0 = never
   DevBuf<int> scSrc;                                // solve-order -> canonical contact index
   DevBuf<int> scState;
   std::vector<int> colorStart;                      // host copy, ncolors+1

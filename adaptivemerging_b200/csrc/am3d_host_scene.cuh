@@ -156,12 +156,12 @@ static void resetState(am3d_ctx* c) {
   c->iterState.ensure(8); c->iterState.zero(8, c->stream);
   c->cur.n = 0; c->prev.n = 0; c->bp.n = 0; c->bpPrev.n = 0; c->cur.nSorted = 0; c->prev.nSorted = 0;
   {
-    // reserve for ~8 contacts and ~4 body pairs per body up front so that steady growth of the contact count (a pile
+    // reserve for ~12 contacts and ~5 body pairs per body up front so that steady growth of the contact count (a pile
     // settling layer by layer) does not reallocate every few steps
-    size_t rc = (size_t)NB * 8 + 4096, rb = (size_t)NB * 4 + 1024;
+    size_t rc = (size_t)NB * 12 + 4096, rb = (size_t)NB * 5 + 1024;
     c->cur.ensure(rc); c->prev.ensure(rc); c->bp.ensure(rb); c->bpPrev.ensure(rb);
     c->hitPos.ensure(3 * rc * 2); c->hitNrm.ensure(3 * rc * 2); c->hitViol.ensure(rc * 2); c->hitMeta.ensure(4 * rc * 2);
-    c->scD.ensure(9 * rc); c->scR.ensure(6 * rc); c->scB.ensure(3 * rc); c->scDiag.ensure(3 * rc); c->scLam.ensure(3 * rc);
+    c->scP.ensure(24 * rc); c->hubDelta.ensure(12 * rb); c->grpDegree.ensure(NS + 1); c->grpHubMask.ensure(rb);
     c->scSrc.ensure(rc); c->scState.ensure(rc);
     c->sgB1.ensure(rb); c->sgB2.ensure(rb); c->sgStart.ensure(rb + 2); c->sgCount.ensure(rb + 2); c->sgFlags.ensure(rb);
     c->sgBpc.ensure(rb); c->sgMass.ensure(20 * rb); c->sgMu.ensure(rb);

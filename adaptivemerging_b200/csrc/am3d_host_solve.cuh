@@ -6,7 +6,7 @@
 
 static SolveArrays solveArrays(am3d_ctx* c) {
   return SolveArrays{c->sgB1.p, c->sgB2.p, c->sgStart.p, c->sgCount.p, c->sgFlags.p, c->sgBpc.p, c->sgMass.p, c->sgMu.p,
-                     c->scD.p, c->scR.p, c->scB.p, c->scDiag.p, c->scLam.p, c->scSrc.p, c->scState.p};
+                     c->scP.p, c->scSrc.p, c->scState.p, c->hubDelta.p};
 }
 static ContactPtrs contactPtrs(ContactSet& S) {
   return ContactPtrs{S.b1.p, S.b2.p, S.s1.p, S.s2.p, S.bv1.p, S.bv2.p, S.info.p, S.leaf.p, S.bpc.p, S.state.p, S.isNew.p,
@@ -18,8 +18,12 @@ static ContactPtrs contactPtrs(ContactSet& S) {
 static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, int inCollection) {
   c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
   c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
+  c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
+  CK(cudaMemsetAsync(c->grpDegree.p, 0, c->NS * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->counters.p + 6, 0, sizeof(int), c->stream));
   LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, inCollection, c->grpSb1.p, c->grpSb2.p,
-         c->grpPrio.p, c->grpColor.p);
+         c->grpPrio.p, c->grpColor.p, c->grpDegree.p);
+  LAUNCH(c, k_grp_hubs, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpDegree.p, c->hubMin, c->grpHubMask.p, c->counters.p + 6);
   CK(cudaMemsetAsync(c->bodyBest.p, 0, c->NS * sizeof(unsigned long long), c->stream));
   CK(cudaMemsetAsync(c->bodyMask.p, 0, c->NS * sizeof(unsigned long long), c->stream));
   CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
@@ -30,8 +34,8 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, in
     while (remaining > 0) {
       for (int r = 0; r < 4; r++) {  // a few rounds per host read-back
         CK(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(int), c->stream));
-        LAUNCH(c, k_color_bid, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p);
-        LAUNCH(c, k_color_assign, nblk(ng), BLK, ng, page, c->grpSb1.p, c->grpSb2.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p,
+        LAUNCH(c, k_color_bid, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpHubMask.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p);
+        LAUNCH(c, k_color_assign, nblk(ng), BLK, ng, page, c->grpSb1.p, c->grpSb2.p, c->grpHubMask.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p,
                c->bodyMask.p, c->counters.p + 2, c->counters.p + 3);
       }
       remaining = readInt(c, c->counters.p + 2);
@@ -56,9 +60,11 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, in
   CK(cudaMemcpyAsync(hist.data(), c->colorHist.p, maxColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->colorStart.clear();
+  c->colorDense.assign(maxColors, -1);
   int acc = 0;
   for (int k = 0; k < maxColors; k++) {
     if (hist[k] == 0) continue;
+    c->colorDense[k] = (int)c->colorStart.size();
     c->colorStart.push_back(acc);
     acc += hist[k];
   }
@@ -98,13 +104,43 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   colourGroups(c, ng, gb1, gb2, sweep ? 1 : 0);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
   c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1);
-  c->scD.ensure(9 * (size_t)nc + 9); c->scR.ensure(6 * (size_t)nc + 6); c->scB.ensure(3 * (size_t)nc + 3);
-  c->scDiag.ensure(3 * (size_t)nc + 3); c->scLam.ensure(3 * (size_t)nc + 3); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1);
+  c->scP.ensure(24 * (size_t)nc + 48); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1); c->hubDelta.ensure(12 * (size_t)ng + 12);
   SolveArrays S = solveArrays(c);
   LAUNCH(c, k_group_setup, nblk(ng), BLK, ng, c->grpOrder.p, c->grpSb1.p, c->grpSb2.p, gb1, gb2, gcount, c->minv.p, c->jinv.p,
-         c->fric.p, c->flags.p, P.friction_override, P.friction, S, c->grpPos.p);
+         c->fric.p, c->flags.p, c->grpHubMask.p, P.friction_override, P.friction, S, c->grpPos.p);
   int nSolve = scanTotal(c, c->sgCount, c->sgStart, ng);  // contacts that take part (sleeping collections excluded)
   c->lastSolveN = nSolve;
+  // hub runs: (colour, hub body) -> the groups of that colour touching the hub, ascending
+  c->nHubRuns = c->nHubEntries = 0;
+  c->colorRunStart.assign(c->nColors + 1, 0);
+  if (readInt(c, c->counters.p + 6) > 0) {
+    c->hubN.ensure(ng + 2); c->hubScan.ensure(ng + 2);
+    LAUNCH(c, k_hub_sides, nblk(ng), BLK, ng, c->sgFlags.p, c->hubN.p);
+    int ne = scanTotal(c, c->hubN, c->hubScan, ng);
+    c->nHubEntries = ne;
+    c->hubKey.ensure(ne + 2); c->hubKeySorted.ensure(ne + 2); c->hubSlot.ensure(ne + 2); c->hubSlotSorted.ensure(ne + 2);
+    c->hubHead.ensure(ne + 2); c->hubRunStart.ensure(ne + 2); c->hubRunBody.ensure(ne + 2); c->hubRunColor.ensure(ne + 2);
+    LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgBpc.p, c->grpColor.p, c->hubScan.p,
+           c->hubKey.p, c->hubSlot.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, 64, c->stream);
+    });
+    LAUNCH(c, k_hub_run_heads, nblk(ne), BLK, ne, c->hubKeySorted.p, c->hubHead.p);
+    int nr = scanTotal(c, c->hubHead, c->hubScan, ne);
+    c->nHubRuns = nr;
+    LAUNCH(c, k_hub_run_fill, nblk(ne), BLK, ne, c->hubKeySorted.p, c->hubHead.p, c->hubScan.p, c->hubRunStart.p, c->hubRunBody.p,
+           c->hubRunColor.p);
+    CK(cudaMemcpyAsync(c->hubRunStart.p + nr, &c->nHubEntries, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> rc(nr);
+    CK(cudaMemcpyAsync(rc.data(), c->hubRunColor.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<int> perColor(c->nColors, 0);
+    for (int r = 0; r < nr; r++) perColor[c->colorDense[rc[r]]]++;
+    for (int k = 0; k < c->nColors; k++) c->colorRunStart[k + 1] = c->colorRunStart[k] + perColor[k];
+    c->hubDelta.ensure(12 * (size_t)ng + 12);
+    S = solveArrays(c);
+  }
+  HubRuns HR{c->hubRunStart.p, c->hubRunBody.p, c->hubSlotSorted.p};
   SolveSet sets[2] = {{&c->cur, 0, 0, !sweep}, {&c->icon, nExt, 1, true}};
   int nsets = sweep ? 2 : 1;
   for (int k = 0; k < nsets; k++) {
@@ -128,9 +164,15 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     CK(cudaMemcpyAsync(c->dColorStart.p, c->colorStart.data(), c->colorStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     int nColors = c->nColors, chk = sweep ? 0 : 1;
     const int* dcs = c->dColorStart.p;
+    const int* dcr = nullptr;
+    if (c->nHubRuns > 0) {
+      c->dColorRunStart.ensure(c->colorRunStart.size() + 1);
+      CK(cudaMemcpyAsync(c->dColorRunStart.p, c->colorRunStart.data(), c->colorRunStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      dcr = c->dColorRunStart.p;
+    }
     double* dvp = c->dv.p;
     unsigned long long* isp = c->iterState.p;
-    void* args[] = {&nColors, &dcs, &S, &dvp, &PP, &iterations, &chk, &isp};
+    void* args[] = {&nColors, &dcs, &dcr, &HR, &S, &dvp, &PP, &iterations, &chk, &isp};
     CK(cudaLaunchCooperativeKernel((void*)k_pgs_persistent, dim3(c->coopBlocks), dim3(128), args, 0, c->stream));
     c->kernelLaunches++;
     c->solveLaunches++;
@@ -138,12 +180,16 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     for (int k = 0; k < c->nColors; k++) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
       LAUNCH(c, k_pgs_color<0>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+      int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
+      if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 0);
     }
     for (int it = 0; it < iterations; it++) {
       int last = it == iterations - 1;
       for (int k = 0; k < c->nColors; k++) {
         int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
         LAUNCH(c, k_pgs_color<1>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
+        if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 1);
         c->solveLaunches++;
       }
       LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);

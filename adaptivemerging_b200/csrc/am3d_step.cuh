@@ -439,10 +439,10 @@ __device__ __forceinline__ unsigned int hash32(unsigned int a) {
   a = a ^ (a >> 15);
   return a;
 }
-// solver bodies of a group: parent collection unless computeInCollection; -1 for a pinned body
+// solver bodies of a group: parent collection unless computeInCollection; negative (-1 - body) for a pinned body
 __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ parent,
                            const int* __restrict__ flags, int inCollection, int* __restrict__ sb1, int* __restrict__ sb2,
-                           unsigned long long* __restrict__ prio, int* __restrict__ color) {
+                           unsigned long long* __restrict__ prio, int* __restrict__ color, int* __restrict__ degree) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   int a = gb1[g], b = gb2[g];
@@ -450,30 +450,51 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
     if (parent[a] >= 0) a = parent[a];
     if (parent[b] >= 0) b = parent[b];
   }
-  sb1[g] = (flags[a] & AM3D_F_PINNED) ? -1 - a : a;  // pinned: encoded negative (still addressable as -1-v)
-  sb2[g] = (flags[b] & AM3D_F_PINNED) ? -1 - b : b;
+  bool pa = flags[a] & AM3D_F_PINNED, pb = flags[b] & AM3D_F_PINNED;
+  sb1[g] = pa ? -1 - a : a;
+  sb2[g] = pb ? -1 - b : b;
+  if (!pa) atomicAdd(degree + a, 1);
+  if (!pb) atomicAdd(degree + b, 1);
   prio[g] = ((unsigned long long)hash32((unsigned)g) << 32) | (unsigned)(g + 1);
   color[g] = -1;
 }
-__global__ void k_color_bid(int ng, const int* __restrict__ sb1, const int* __restrict__ sb2,
+// Hubs: non-pinned solver bodies touched by >= hubMin groups (a funnel, a big merged collection).  A hub side takes
+// no part in the colouring (like a pinned body); its deltaV is updated once per colour from the per-group deltas.
+__global__ void k_grp_hubs(int ng, const int* __restrict__ sb1, const int* __restrict__ sb2, const int* __restrict__ degree,
+                           int hubMin, int* __restrict__ hubMask, int* __restrict__ nHubSides) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  int m = 0;
+  if (hubMin > 0) {
+    if (sb1[g] >= 0 && degree[sb1[g]] >= hubMin) m |= 1;
+    if (sb2[g] >= 0 && degree[sb2[g]] >= hubMin) m |= 2;
+  }
+  hubMask[g] = m;
+  if (m) atomicAdd(nHubSides, (m & 1) + ((m >> 1) & 1));
+}
+__global__ void k_color_bid(int ng, const int* __restrict__ sb1, const int* __restrict__ sb2, const int* __restrict__ hubMask,
                             const unsigned long long* __restrict__ prio, const int* __restrict__ color,
                             unsigned long long* __restrict__ best) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng || color[g] != -1) return;
   unsigned long long p = prio[g];
-  if (sb1[g] >= 0) atomicMax(best + sb1[g], p);
-  if (sb2[g] >= 0) atomicMax(best + sb2[g], p);
+  int hm = hubMask[g];
+  if (sb1[g] >= 0 && !(hm & 1)) atomicMax(best + sb1[g], p);
+  if (sb2[g] >= 0 && !(hm & 2)) atomicMax(best + sb2[g], p);
 }
 // page = which block of 64 colours is being filled; groups whose bodies have no free colour left in this
 // page are deferred to the next one (color = -2 - page marks "waiting for page+1")
 __global__ void k_color_assign(int ng, int page, const int* __restrict__ sb1, const int* __restrict__ sb2,
-                               const unsigned long long* __restrict__ prio, int* __restrict__ color,
+                               const int* __restrict__ hubMask, const unsigned long long* __restrict__ prio, int* __restrict__ color,
                                unsigned long long* __restrict__ best, unsigned long long* __restrict__ mask,
                                int* __restrict__ remaining, int* __restrict__ deferred) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng || color[g] != -1) return;
   unsigned long long p = prio[g];
   int a = sb1[g], b = sb2[g];
+  int hm = hubMask[g];
+  if (hm & 1) a = -1;  // hub sides do not constrain the colour
+  if (hm & 2) b = -1;
   bool win = (a < 0 || best[a] == p) && (b < 0 || best[b] == p);
   if (!win) { atomicAdd(remaining, 1); return; }
   unsigned long long m = (a >= 0 ? mask[a] : 0ULL) | (b >= 0 ? mask[b] : 0ULL);
@@ -509,17 +530,21 @@ __global__ void k_color_sortkey(int ng, const int* __restrict__ color, unsigned 
 struct SolveArrays {
   int *sgB1, *sgB2, *sgStart, *sgCount, *sgFlags, *sgBpc;
   double *sgMass, *sgMu;
-  double *scD, *scR, *scB, *scDiag, *scLam;
+  double* scP;       // [24] per contact, solve order: n t1 t2 (9) | r1 r2 (6) | b (3) | D (3) | lambda (3)
   int *scSrc, *scState;
+  double* hubDelta;  // [12] per group: what this group added to a hub body on side 1 / side 2 in the current colour
 };
+#define SG_CLAMP 1
+#define SG_HUB1 2
+#define SG_HUB2 4
 
 // one thread per group in solve order: gather body data (mass packet, friction, magnet flags)
 __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos -> group */, const int* __restrict__ sb1,
                               const int* __restrict__ sb2, const int* __restrict__ gb1, const int* __restrict__ gb2,
                               const int* __restrict__ gcount, const double* __restrict__ minv,
                               const double* __restrict__ jinv, const double* __restrict__ fric,
-                              const int* __restrict__ flags, int frictionOverride, double frictionVal, SolveArrays S,
-                              int* __restrict__ grpPos) {
+                              const int* __restrict__ flags, const int* __restrict__ hubMask, int frictionOverride,
+                              double frictionVal, SolveArrays S, int* __restrict__ grpPos) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ng) return;
   int g = order[p];
@@ -547,7 +572,7 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
   S.sgMu[p] = mu;
   int fl1 = flags[l1], fl2 = flags[l2];
   bool clamp = (!(fl1 & AM3D_F_MAGNETIC) || !(fl1 & AM3D_F_MAGNET_ACTIVE)) && (!(fl2 & AM3D_F_MAGNETIC) || !(fl2 & AM3D_F_MAGNET_ACTIVE));
-  S.sgFlags[p] = clamp ? 1 : 0;
+  S.sgFlags[p] = (clamp ? SG_CLAMP : 0) | ((hubMask[g] & 1) ? SG_HUB1 : 0) | ((hubMask[g] & 2) ? SG_HUB2 : 0);
 }
 
 // Contact.computeJacobian :235-271, computeB :279-326, computeJMinvJt :340-354; one thread per contact,
@@ -594,9 +619,9 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
     p = ld3(pW + 3 * i); n = ld3(nW + 3 * i); t1 = ld3(t1W + 3 * i); t2 = ld3(t2W + 3 * i);
   }
   d3 r1 = vsub(p, ld3(x + 3 * a)), r2 = vsub(p, ld3(x + 3 * b));
-  double* D = S.scD + 9 * idx;
-  st3(D, n); st3(D + 3, t1); st3(D + 6, t2);
-  st3(S.scR + 6 * idx, r1); st3(S.scR + 6 * idx + 3, r2);
+  double* PK = S.scP + 24 * (size_t)idx;
+  st3(PK, n); st3(PK + 3, t1); st3(PK + 6, t2);
+  st3(PK + 9, r1); st3(PK + 12, r2);
   // Jacobian rows
   d3 dir[3] = {n, t1, t2};
   d3 jaw[3], jbw[3];
@@ -633,13 +658,13 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
     bb[0] += bBounce;
     bb[0] += feedback * viol[i];
   }
-  S.scB[3 * idx] = bb[0]; S.scB[3 * idx + 1] = bb[1]; S.scB[3 * idx + 2] = bb[2];
+  PK[15] = bb[0]; PK[16] = bb[1]; PK[17] = bb[2];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     d3 jav = vscale(-1, dir[k]);
     d3 tmp1 = mtransform(J1, jaw[k]), tmp2 = mtransform(J2, jbw[k]);
-    S.scDiag[3 * idx + k] = mi1 * vdot(jav, jav) + vdot(jaw[k], tmp1) + mi2 * vdot(dir[k], dir[k]) + vdot(jbw[k], tmp2);
-    S.scLam[3 * idx + k] = lam[3 * i + k];
+    PK[18 + k] = mi1 * vdot(jav, jav) + vdot(jaw[k], tmp1) + mi2 * vdot(dir[k], dir[k]) + vdot(jbw[k], tmp2);
+    PK[21 + k] = lam[3 * i + k];
   }
   S.scSrc[idx] = i | (setId << 30);
   S.scState[idx] = cstate[i];
@@ -669,37 +694,52 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
 }
 
 // One body-pair group: its contacts in sequence, the deltaV of its two solver bodies held in registers.
-// MODE 0: confidentWarmStart (PGS.java:250-256); MODE 1: one Gauss-Seidel sweep (:105-181)
+// MODE 0: confidentWarmStart (PGS.java:250-256); MODE 1: one Gauss-Seidel sweep (:105-181).
+// A hub side works on a private copy of the hub's deltaV as of the start of the colour (plus this group's own
+// updates) and hands what it added to hubDelta; k_hub_reduce folds the deltas in after the colour, in a fixed order.
+__device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int MODE>
 __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
                                          double& localMax) {
   int a = S.sgB1[p], b = S.sgB2[p];
   int start = S.sgStart[p], cnt = S.sgCount[p];
+  const double* PK0 = S.scP + 24 * (size_t)start;
+  if (cnt > 0) { prefetchL2(PK0); prefetchL2(PK0 + 16); }
   double M[20];
   const double* Mp = S.sgMass + 20 * p;
 #pragma unroll
   for (int k = 0; k < 20; k++) M[k] = Mp[k];
   double mu = S.sgMu[p];
-  bool clamp = S.sgFlags[p] & 1;
-  double dv1[6], dv2[6];
+  int fl = S.sgFlags[p];
+  bool clamp = fl & SG_CLAMP;
+  bool hubA = fl & SG_HUB1, hubB = fl & SG_HUB2;
+  double dv1[6], dv2[6], acc1[6], acc2[6];
 #pragma unroll
-  for (int k = 0; k < 6; k++) { dv1[k] = a >= 0 ? __ldcg(dv + 6 * a + k) : 0.0; dv2[k] = b >= 0 ? __ldcg(dv + 6 * b + k) : 0.0; }
+  for (int k = 0; k < 6; k++) {
+    dv1[k] = a >= 0 ? __ldcg(dv + 6 * a + k) : 0.0;
+    dv2[k] = b >= 0 ? __ldcg(dv + 6 * b + k) : 0.0;
+    acc1[k] = 0.0;
+    acc2[k] = 0.0;
+  }
   for (int c = 0; c < cnt; c++) {
-    int idx = start + c;
-    const double* Dp = S.scD + 9 * idx;
-    d3 dir[3] = {ld3(Dp), ld3(Dp + 3), ld3(Dp + 6)};
-    d3 r1 = ld3(S.scR + 6 * idx), r2 = ld3(S.scR + 6 * idx + 3);
-    double lam[3] = {S.scLam[3 * idx], S.scLam[3 * idx + 1], S.scLam[3 * idx + 2]};
+    double* PK = S.scP + 24 * (size_t)(start + c);
+    if (c + 1 < cnt) { prefetchL2(PK + 24); prefetchL2(PK + 40); }  // next contact: hide the load latency of the sequential chain
+    d3 dir[3] = {ld3(PK), ld3(PK + 3), ld3(PK + 6)};
+    d3 r1 = ld3(PK + 9), r2 = ld3(PK + 12);
+    double lam[3] = {PK[21], PK[22], PK[23]};
     if (MODE == 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
         if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, lam[k]);
         if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, lam[k]);
+        if (hubA) applyRow(acc1, M[0], M + 1, jav, jaw, lam[k]);
+        if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, lam[k]);
       }
     } else {
-      double bb[3] = {S.scB[3 * idx], S.scB[3 * idx + 1], S.scB[3 * idx + 2]};
-      double DD[3] = {S.scDiag[3 * idx], S.scDiag[3 * idx + 1], S.scDiag[3 * idx + 2]};
+      double bb[3] = {PK[15], PK[16], PK[17]};
+      double DD[3] = {PK[18], PK[19], PK[20]};
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
@@ -718,9 +758,11 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
         double diff = l - prev;
         if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
         if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
+        if (hubA) applyRow(acc1, M[0], M + 1, jav, jaw, diff);
+        if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, diff);
         localMax = fmax(localMax, fabs(diff));
       }
-      S.scLam[3 * idx] = lam[0]; S.scLam[3 * idx + 1] = lam[1]; S.scLam[3 * idx + 2] = lam[2];
+      PK[21] = lam[0]; PK[22] = lam[1]; PK[23] = lam[2];
       if (lastIter) {
         // Contact.updateContactState :385-398
         d3 jaw1 = vcross(dir[1], r1), jbw1 = vcross(r2, dir[1]);
@@ -732,18 +774,61 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
         else if (fabs(w1) > P.sliding) st = AM3D_CS_ONEDGE;
         else if (fabs(w2) > P.sliding) st = AM3D_CS_ONEDGE;
         else st = AM3D_CS_CLEAR;
-        S.scState[idx] = st;
+        S.scState[start + c] = st;
       }
     }
   }
   if (a >= 0) {
+    if (!hubA) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+      for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + k] = acc1[k];
+    }
   }
   if (b >= 0) {
+    if (!hubB) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+      for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + 6 + k] = acc2[k];
+    }
   }
+}
+
+// Fold the per-group deltas of one colour into the hubs' deltaV: one warp per (colour, hub) run, lanes take the
+// run's entries strided by 32 (sequential partial sums), then a fixed xor-butterfly: the order never changes.
+struct HubRuns {
+  const int* runStart;   // [nRuns + 1] into entrySlot
+  const int* runBody;    // [nRuns] hub solver body
+  const int* entrySlot;  // group * 2 + side, ascending group within a run
+};
+__device__ __forceinline__ void hubReduceRun(int r, const HubRuns& H, const double* __restrict__ hubDelta, double* __restrict__ dv) {
+  int lane = threadIdx.x & 31;
+  int e0 = H.runStart[r], e1 = H.runStart[r + 1];
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = e0 + lane; e < e1; e += 32) {
+    int slot = H.entrySlot[e];
+    const double* d = hubDelta + 6 * (size_t)slot;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s[k] = s[k] + __ldcg(d + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    for (int o = 16; o > 0; o >>= 1) s[k] = s[k] + __shfl_xor_sync(0xffffffffu, s[k], o);
+  if (lane == 0) {
+    int h = H.runBody[r];
+#pragma unroll
+    for (int k = 0; k < 6; k++) dv[6 * h + k] = __ldcg(dv + 6 * h + k) + s[k];
+  }
+}
+__global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __restrict__ hubDelta, double* __restrict__ dv,
+                             const unsigned long long* __restrict__ iterState, int mode) {
+  if (mode == 1 && iterState[1]) return;
+  int r = rBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (r < rEnd) hubReduceRun(r, H, hubDelta, dv);
 }
 
 template <int MODE>
@@ -762,18 +847,27 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
 }
 
 // The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
-// colour.  Used when the colours are many and small (merged collections are hubs of the contact graph, batched
-// scenes): thousands of tiny launches become grid syncs.  Same Gauss-Seidel sequence as the per-colour launches.
+// colour (two when the colour has hub runs).  Used when the colours are many and small (batched scenes): thousands
+// of tiny launches become grid syncs.  Same Gauss-Seidel sequence as the per-colour launches.
 __global__ void __launch_bounds__(128)
-k_pgs_persistent(int nColors, const int* __restrict__ colorStart, SolveArrays S, double* __restrict__ dv, PgsParams P,
-                 int iterations, int checkTolerance, unsigned long long* __restrict__ iterState) {
+k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H,
+                 SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance,
+                 unsigned long long* __restrict__ iterState) {
   cg::grid_group grid = cg::this_grid();
   int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  int warp = tid >> 5, nwarps = stride >> 5;
   double dummy = 0;
   for (int c = 0; c < nColors; c++) {
     int g1 = colorStart[c + 1];
     for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0>(p, S, dv, P, 0, dummy);
     grid.sync();
+    if (colorRunStart) {
+      int r1 = colorRunStart[c + 1];
+      if (r1 > colorRunStart[c]) {
+        for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);
+        grid.sync();
+      }
+    }
   }
   for (int it = 0; it < iterations; it++) {
     int last = it == iterations - 1;
@@ -782,6 +876,13 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, SolveArrays S,
       int g1 = colorStart[c + 1];
       for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1>(p, S, dv, P, last, localMax);
       grid.sync();
+      if (colorRunStart) {
+        int r1 = colorRunStart[c + 1];
+        if (r1 > colorRunStart[c]) {
+          for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);
+          grid.sync();
+        }
+      }
     }
     for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
     if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
@@ -797,6 +898,42 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, SolveArrays S,
     if (((volatile unsigned long long*)iterState)[1]) break;
   }
 }
+
+// hub entries: one per (group, hub side), keyed (colour, hub body, group position) so that a radix sort groups them
+// into (colour, hub) runs with ascending group position
+__global__ void k_hub_entries(int ng, const int* __restrict__ sgFlags, const int* __restrict__ sgB1, const int* __restrict__ sgB2,
+                              const int* __restrict__ sgBpc, const int* __restrict__ grpColor, const int* __restrict__ scan,
+                              unsigned long long* __restrict__ key, int* __restrict__ slot) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  int fl = sgFlags[p];
+  int o = scan[p];
+  unsigned long long col = (unsigned long long)grpColor[sgBpc[p]];
+  if (fl & SG_HUB1) { key[o] = (col << 52) | ((unsigned long long)sgB1[p] << 26) | (unsigned long long)p; slot[o] = 2 * p; o++; }
+  if (fl & SG_HUB2) { key[o] = (col << 52) | ((unsigned long long)sgB2[p] << 26) | (unsigned long long)p; slot[o] = 2 * p + 1; }
+}
+__global__ void k_hub_sides(int ng, const int* __restrict__ sgFlags, int* __restrict__ n) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  int fl = sgFlags[p];
+  n[p] = ((fl & SG_HUB1) ? 1 : 0) + ((fl & SG_HUB2) ? 1 : 0);
+}
+__global__ void k_hub_run_heads(int ne, const unsigned long long* __restrict__ key, int* __restrict__ head) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  head[e] = (e == 0 || (key[e] >> 26) != (key[e - 1] >> 26)) ? 1 : 0;
+}
+__global__ void k_hub_run_fill(int ne, const unsigned long long* __restrict__ key, const int* __restrict__ head,
+                               const int* __restrict__ scan, int* __restrict__ runStart, int* __restrict__ runBody,
+                               int* __restrict__ runColor) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne || !head[e]) return;
+  int r = scan[e];
+  runStart[r] = e;
+  runBody[r] = (int)((key[e] >> 26) & 0x3ffffff);
+  runColor[r] = (int)(key[e] >> 52);
+}
+
 __global__ void k_iter_end(unsigned long long* iterState, double tolerance, int checkTolerance) {
   if (iterState[1]) return;
   iterState[2] += 1;
@@ -815,13 +952,14 @@ __global__ void k_post_solve(int nc, SolveArrays S, const int* __restrict__ cbpc
   if (idx >= nc) return;
   int src = S.scSrc[idx];
   int set = src >> 30, i = src & 0x3fffffff;
-  double l0 = S.scLam[3 * idx];
+  const double* PK = S.scP + 24 * (size_t)idx;
+  double l0 = PK[21];
   if (set == 0) {
-    if (writeLam0) { lam0[3 * i] = l0; lam0[3 * i + 1] = S.scLam[3 * idx + 1]; lam0[3 * i + 2] = S.scLam[3 * idx + 2]; }
+    if (writeLam0) { lam0[3 * i] = l0; lam0[3 * i + 1] = PK[22]; lam0[3 * i + 2] = PK[23]; }
     state0[i] = S.scState[idx];
     if (nActive && cbpc0[i] >= 0 && fabs(l0) > 1e-14) atomicAdd(nActive + cbpc0[i], 1);  // clearBodyPairContacts :213-226
   } else {
-    lam1[3 * i] = l0; lam1[3 * i + 1] = S.scLam[3 * idx + 1]; lam1[3 * i + 2] = S.scLam[3 * idx + 2];
+    lam1[3 * i] = l0; lam1[3 * i + 1] = PK[22]; lam1[3 * i + 2] = PK[23];
     state1[i] = S.scState[idx];
   }
 }
@@ -995,4 +1133,21 @@ __global__ void k_tail_keys(int nt, int base, const unsigned long long* __restri
   if (i >= nt) return;
   k[i] = key0[base + i];
   v[i] = base + i;
+}
+
+// bulk velocity pokes from the host (MouseImpulse / Animation style inputs): added to the top-level entity
+__global__ void k_add_velocities(int nb, const int* __restrict__ parent, const double* __restrict__ dvl,
+                                 const double* __restrict__ dwl, double* __restrict__ v, double* __restrict__ w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  d3 a = ld3(dvl + 3 * i), b = ld3(dwl + 3 * i);
+  if (a.x == 0 && a.y == 0 && a.z == 0 && b.x == 0 && b.y == 0 && b.z == 0) return;
+  int t = parent[i] >= 0 ? parent[i] : i;
+  if (t == i) {
+    st3(v + 3 * i, vadd(ld3(v + 3 * i), a));
+    st3(w + 3 * i, vadd(ld3(w + 3 * i), b));
+  } else {
+    atomicAdd(v + 3 * t, a.x); atomicAdd(v + 3 * t + 1, a.y); atomicAdd(v + 3 * t + 2, a.z);
+    atomicAdd(w + 3 * t, b.x); atomicAdd(w + 3 * t + 1, b.y); atomicAdd(w + 3 * t + 2, b.z);
+  }
 }

@@ -95,6 +95,7 @@ class am3d_contact(C.Structure):
         ("body1", C.c_int32), ("body2", C.c_int32), ("csb1", C.c_int32), ("csb2", C.c_int32),
         ("bv1", C.c_int32), ("bv2", C.c_int32), ("info", C.c_int32), ("leaf", C.c_int32),
         ("state", C.c_int32), ("new_this_step", C.c_int32), ("color", C.c_int32), ("in_collection", C.c_int32),
+        ("hub_mask", C.c_int32), ("_pad", C.c_int32),
         ("contactB1", C.c_double * 3), ("normalB1", C.c_double * 3), ("tangent1B1", C.c_double * 3),
         ("tangent2B1", C.c_double * 3), ("point_w", C.c_double * 3), ("normal_w", C.c_double * 3),
         ("violation", C.c_double), ("prev_violation", C.c_double),
@@ -115,7 +116,7 @@ import numpy as np  # noqa: E402
 CONTACT_DTYPE = np.dtype([
     ("body1", "<i4"), ("body2", "<i4"), ("csb1", "<i4"), ("csb2", "<i4"), ("bv1", "<i4"), ("bv2", "<i4"),
     ("info", "<i4"), ("leaf", "<i4"), ("state", "<i4"), ("new_this_step", "<i4"), ("color", "<i4"),
-    ("in_collection", "<i4"),
+    ("in_collection", "<i4"), ("hub_mask", "<i4"), ("_pad", "<i4"),
     ("contactB1", "<f8", 3), ("normalB1", "<f8", 3), ("tangent1B1", "<f8", 3), ("tangent2B1", "<f8", 3),
     ("point_w", "<f8", 3), ("normal_w", "<f8", 3), ("violation", "<f8"), ("prev_violation", "<f8"),
     ("lambda", "<f8", 3), ("lambda_warm", "<f8", 3),

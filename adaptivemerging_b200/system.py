@@ -137,6 +137,12 @@ class RigidBodySystem:
         w = np.ascontiguousarray(domega, np.float64) if domega is not None else None
         self._ck(self._L.am3d_add_body_velocity(self._h, int(body), _p(v), _p(w)))
 
+    def add_velocities(self, dv, domega):
+        """bulk velocity pokes, [n,3] each (the batched form of MouseImpulse / scripted pushes)"""
+        dv = np.ascontiguousarray(dv, np.float64)
+        dw = np.ascontiguousarray(domega, np.float64)
+        self._ck(self._L.am3d_add_velocities(self._h, _p(dv), _p(dw)))
+
     def contacts(self, include_internal=False):
         n = self._L.am3d_num_contacts(self._h, int(include_internal))
         out = np.zeros(max(n, 1), CONTACT_DTYPE)
@@ -193,6 +199,9 @@ class RigidBodySystem:
         self._ck(self._L.am3d_download_collection(self._h, int(slot), _p(out)))
         return dict(x=out[0:3], R=out[3:12], v=out[12:15], omega=out[15:18], mass=out[18], minv=out[19], jinv=out[20:29],
                     mA=out[29:38], flags=int(out[38]), alive=int(out[39]), count=int(out[40]), stamp=int(out[41]))
+
+    def set_option(self, name, value):
+        self._ck(self._L.am3d_set_option(self._h, name.encode(), float(value)))
 
     def mark(self, slot):
         self._ck(self._L.am3d_mark(self._h, int(slot)))

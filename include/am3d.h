@@ -233,6 +233,8 @@ typedef struct am3d_contact {
   int32_t new_this_step;
   int32_t color;        /* colour of the full solve (-1 if not solved) */
   int32_t in_collection;/* 1 if this is an internal contact of a collection */
+  int32_t hub_mask;     /* solve-order lists only: bit 0 / 1 = body1 / body2 side was treated as a hub */
+  int32_t _pad;
   double contactB1[3], normalB1[3], tangent1B1[3], tangent2B1[3];
   double point_w[3], normal_w[3]; /* world frame at detection time */
   double violation, prev_violation;
@@ -275,6 +277,8 @@ int am3d_sync(am3d_ctx* ctx);
  * (LCPApp3D scripted pushes, MouseImpulse, Animation) */
 int am3d_set_body_velocity(am3d_ctx* ctx, int body, const double v[3], const double omega[3]);
 int am3d_add_body_velocity(am3d_ctx* ctx, int body, const double dv[3], const double domega[3]);
+/* bulk version: per-body velocity increments [3n] each (zeros are skipped), added to the top-level entity */
+int am3d_add_velocities(am3d_ctx* ctx, const double* dv, const double* domega);
 int am3d_upload_bodies(am3d_ctx* ctx, const double* x, const double* R, const double* v,
                        const double* omega); /* teacher forcing: overwrite the state of all leaf bodies */
 
@@ -321,6 +325,9 @@ int am3d_num_internal_bpcs(am3d_ctx* ctx);
 int am3d_download_internal_bpcs(am3d_ctx* ctx, am3d_bpc* out, int capacity, int* count);
 /* one RigidCollection: x[3] R[9] v[3] omega[3] mass minv jinv[9] massAngular[9] flags alive members stamp */
 int am3d_download_collection(am3d_ctx* ctx, int slot, double* out42);
+/* engine options that are not reference parameters: "hub_min_degree" (body pairs per body from which a body is a
+ * hub of the contact graph, 0 = never; default 64), "pgs_persistent" (0 never / 1 heuristic / 2 always) */
+int am3d_set_option(am3d_ctx* ctx, const char* name, double value);
 int am3d_mark(am3d_ctx* ctx, int slot);
 int am3d_elapsed_ms(am3d_ctx* ctx, double* ms);
 /* order (position in the Gauss-Seidel sequence) the full solve gave each

@@ -304,6 +304,149 @@ struct System {
     if (!computeInCollection) lastIterations = executed;
   }
 
+
+  // ------------------------------------------------------------------------------------------------
+  // Replay of the CUDA path's solve when it used HUB bodies: not part of the reference.
+  // The supplied sequence is colour-major; consecutive contacts of one body pair form a group.  A group works on a
+  // private copy of a hub body's deltaV (its value at the start of the colour plus the group's own updates) and
+  // records what it added; after the colour the recorded deltas are folded into the hub in the GPU's fixed order
+  // (32 strided partial sums, then an xor butterfly).  Without hub flags this is exactly pgsSolve.
+  // ------------------------------------------------------------------------------------------------
+  struct OrderMeta { int color; int hub; };
+  static void applyRowTo(V6& dv, const Body* body, const V6& j, double lambda) {
+    dv.v = scaleAdd(body->minv * lambda, j.v, dv.v);
+    V3 tmp = transform(body->jinv, j.w);
+    dv.w = scaleAdd(lambda, tmp, dv.w);
+  }
+  static V6 warpSum(const std::vector<V6>& vals) {
+    double part[32][6];
+    for (int l = 0; l < 32; l++) for (int k = 0; k < 6; k++) part[l][k] = 0.0;
+    for (size_t e = 0; e < vals.size(); e++) {
+      const V6& d = vals[e];
+      double x[6] = {d.v.x, d.v.y, d.v.z, d.w.x, d.w.y, d.w.z};
+      for (int k = 0; k < 6; k++) part[e % 32][k] = part[e % 32][k] + x[k];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      double nw[32][6];
+      for (int l = 0; l < 32; l++) for (int k = 0; k < 6; k++) nw[l][k] = part[l][k] + part[l ^ o][k];
+      std::memcpy(part, nw, sizeof(part));
+    }
+    V6 r;
+    r.v = V3(part[0][0], part[0][1], part[0][2]);
+    r.w = V3(part[0][3], part[0][4], part[0][5]);
+    return r;
+  }
+  template <class Fn>
+  void hubSweep(std::vector<Contact*>& list, const std::vector<OrderMeta>& meta, bool cic, Fn fn) {
+    size_t i = 0, n = list.size();
+    auto sb = [&](Contact* c, int side) {
+      Body* b = side == 0 ? c->body1 : c->body2;
+      return (b->isInCollection() && !cic) ? b->parent : b;
+    };
+    while (i < n) {
+      int col = meta[i].color;
+      size_t cend = i;
+      while (cend < n && meta[cend].color == col) cend++;
+      std::vector<std::pair<Body*, std::vector<V6>>> pending;
+      auto pend = [&](Body* h, const V6& d) {
+        for (auto& kv : pending) if (kv.first == h) { kv.second.push_back(d); return; }
+        pending.push_back({h, std::vector<V6>{d}});
+      };
+      size_t g = i;
+      while (g < cend) {
+        size_t ge = g;
+        while (ge < cend && list[ge]->body1 == list[g]->body1 && list[ge]->body2 == list[g]->body2) ge++;
+        Body *s1 = sb(list[g], 0), *s2 = sb(list[g], 1);
+        bool h1 = (meta[g].hub & 1) != 0, h2 = (meta[g].hub & 2) != 0;
+        V6 loc1 = s1->deltaV, loc2 = s2->deltaV, acc1, acc2;
+        for (size_t k = g; k < ge; k++)
+          fn(list[k], s1, s2, h1 ? &loc1 : &s1->deltaV, h2 ? &loc2 : &s2->deltaV, h1 ? &acc1 : nullptr, h2 ? &acc2 : nullptr);
+        if (h1) pend(s1, acc1);
+        if (h2) pend(s2, acc2);
+        g = ge;
+      }
+      for (auto& kv : pending) {
+        V6 t = warpSum(kv.second);
+        V6& d = kv.first->deltaV;
+        d.v = V3(d.v.x + t.v.x, d.v.y + t.v.y, d.v.z + t.v.z);
+        d.w = V3(d.w.x + t.w.x, d.w.y + t.w.y, d.w.z + t.w.z);
+      }
+      i = cend;
+    }
+  }
+  void pgsSolveHub(std::vector<Contact*>& list, const std::vector<OrderMeta>& meta, double dt, int iterations, double tolerance,
+                   double omega, double feedbackStiffness, double compliance, bool computeInCollection) {
+    if (list.empty()) return;
+    const bool cic = computeInCollection;
+    auto rows = [](Contact* c, int k, const V6*& ja, const V6*& jb) {
+      ja = &c->jna; jb = &c->jnb;
+      if (k == 1) { ja = &c->jt1a; jb = &c->jt1b; } else if (k == 2) { ja = &c->jt2a; jb = &c->jt2b; }
+    };
+    hubSweep(list, meta, cic, [&](Contact* c, Body* s1, Body* s2, V6* d1, V6* d2, V6* a1, V6* a2) {
+      double lam[3] = {c->lambda0, c->lambda1, c->lambda2};
+      for (int k = 0; k < 3; k++) {
+        const V6 *ja, *jb;
+        rows(c, k, ja, jb);
+        applyRowTo(*d1, s1, *ja, lam[k]);
+        applyRowTo(*d2, s2, *jb, lam[k]);
+        if (a1) applyRowTo(*a1, s1, *ja, lam[k]);
+        if (a2) applyRowTo(*a2, s2, *jb, lam[k]);
+      }
+    });
+    for (Contact* c : list) {
+      computeB(c, dt, feedbackStiffness, cic, P.restitution_override != 0, P.restitution);
+      computeJMinvJt(c, cic);
+    }
+    int iter = iterations, executed = 0;
+    while (iter > 0) {
+      double lambdaChangeAbsMax = 0;
+      hubSweep(list, meta, cic, [&](Contact* contact, Body* s1, Body* s2, V6* d1, V6* d2, V6* a1, V6* a2) {
+        bool clamp = (!contact->body1->magnetic || !contact->body1->activateMagnet) &&
+                     (!contact->body2->magnetic || !contact->body2->activateMagnet);
+        double mu;
+        if (P.friction_override) mu = P.friction;
+        else {
+          double f1 = contact->body1->friction, f2 = contact->body2->friction;
+          if (f1 < 0.2 || f2 < 0.2) mu = std::min(f1, f2);
+          else if (f1 > 1. || f2 > 1.) mu = std::max(f1, f2);
+          else mu = (f1 + f2) / 2.;
+        }
+        double* lam[3] = {&contact->lambda0, &contact->lambda1, &contact->lambda2};
+        double bb[3] = {contact->bn, contact->bt1, contact->bt2}, DD[3] = {contact->D00, contact->D11, contact->D22};
+        for (int k = 0; k < 3; k++) {
+          const V6 *ja, *jb;
+          rows(contact, k, ja, jb);
+          double Jdv = dot6(*ja, *d1) + dot6(*jb, *d2);
+          double prev = *lam[k];
+          double l = (DD[k] * prev - omega * (bb[k] + Jdv)) / (DD[k] + compliance);
+          if (clamp) {
+            if (k == 0) l = std::max(0.0, l);
+            else { double limit = mu * contact->lambda0; l = std::max(l, -limit); l = std::min(l, limit); }
+          }
+          *lam[k] = l;
+          double diff = l - prev;
+          applyRowTo(*d1, s1, *ja, diff);
+          applyRowTo(*d2, s2, *jb, diff);
+          if (a1) applyRowTo(*a1, s1, *ja, diff);
+          if (a2) applyRowTo(*a2, s2, *jb, diff);
+          lambdaChangeAbsMax = std::max(lambdaChangeAbsMax, std::fabs(diff));
+        }
+        if (iter == 1) {
+          contact->w1 = contact->bt1 + (dot6(contact->jt1a, *d1) + dot6(contact->jt1b, *d2));
+          contact->w2 = contact->bt2 + (dot6(contact->jt2a, *d1) + dot6(contact->jt2b, *d2));
+          if (std::fabs(contact->lambda0) <= 1e-14) contact->state = BROKEN;
+          else if (std::fabs(contact->w1) > P.sliding_threshold) contact->state = ONEDGE;
+          else if (std::fabs(contact->w2) > P.sliding_threshold) contact->state = ONEDGE;
+          else contact->state = CLEAR;
+        }
+      });
+      iter--;
+      executed++;
+      if (!cic && lambdaChangeAbsMax < tolerance) break;
+    }
+    if (!cic) lastIterations = executed;
+  }
+
   // ==========================================================================================
   // collision detection: CollisionProcessor.java
   // ==========================================================================================
@@ -1388,11 +1531,15 @@ struct System {
     return k;
   }
   // re-order `list` to follow the externally supplied key sequence (the CUDA path's colour order)
-  void applyOrder(std::vector<Contact*>& list, const std::vector<am3d_contact>& order) {
+  // returns true if the supplied sequence carries hub flags (then `meta` is aligned with the re-ordered list)
+  bool applyOrder(std::vector<Contact*>& list, const std::vector<am3d_contact>& order, std::vector<OrderMeta>& meta) {
     std::map<FullKey, std::vector<Contact*>> byKey;
     for (Contact* c : list) byKey[fullKey(c)].push_back(c);
     std::vector<Contact*> out;
     std::set<Contact*> used;
+    meta.clear();
+    bool anyHub = false;
+    int lastColor = 0;
     for (const am3d_contact& k : order) {
       FullKey fk{{k.body1, k.body2, k.csb1, k.csb2, k.bv1, k.bv2, k.info, k.leaf}};
       auto it = byKey.find(fk);
@@ -1401,10 +1548,14 @@ struct System {
       it->second.erase(it->second.begin());
       out.push_back(c);
       used.insert(c);
+      meta.push_back(OrderMeta{k.color, k.hub_mask});
+      lastColor = k.color;
+      if (k.hub_mask) anyHub = true;
     }
     for (Contact* c : list)
-      if (!used.count(c)) { orderMismatch++; out.push_back(c); }
+      if (!used.count(c)) { orderMismatch++; out.push_back(c); meta.push_back(OrderMeta{lastColor + 1, 0}); }
     list = out;
+    return anyHub;
   }
 
   // updateInCollections :232-303
@@ -1425,10 +1576,12 @@ struct System {
         if (body->isCollection && !body->sleeping)
           list.insert(list.end(), body->internalContacts.begin(), body->internalContacts.end());
     }
-    if (haveOrderSweep) applyOrder(list, orderSweep);
+    std::vector<OrderMeta> meta;
+    bool hubs = haveOrderSweep && applyOrder(list, orderSweep, meta);
     updateJacobiansThatNeedUpdating(list, true);
     double t2 = nowSec();
-    pgsSolve(list, dt, P.iterations_in_collection, 1e-5, 1., P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., true);
+    if (hubs) pgsSolveHub(list, meta, dt, P.iterations_in_collection, 1e-5, 1., P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., true);
+    else pgsSolve(list, dt, P.iterations_in_collection, 1e-5, 1., P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., true);
     T.single_it_pgs = nowSec() - t2;
     lastSweepList = list;
     for (Body* body : bodies) {
@@ -1447,10 +1600,12 @@ struct System {
       // the externally supplied sequence only orders the Gauss-Seidel sweeps; `contacts` itself keeps the
       // reference's emission order (it decides which duplicate-key contact the warm-start map retains, :443-448)
       std::vector<Contact*> list = contacts;
-      if (haveOrderFull) applyOrder(list, orderFull);
+      std::vector<OrderMeta> meta;
+      bool hubs = haveOrderFull && applyOrder(list, orderFull, meta);
       updateJacobiansThatNeedUpdating(list, false);
       double t0 = nowSec();
-      pgsSolve(list, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
+      if (hubs) pgsSolveHub(list, meta, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
+      else pgsSolve(list, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
       T.lcp_solve = nowSec() - t0;
       T.pgs_iterations = lastIterations;
       rowUpdates += 3L * (long)contacts.size() * lastIterations;
@@ -1728,6 +1883,7 @@ struct System {
     o->bv1 = c->bv1; o->bv2 = c->bv2; o->info = c->info; o->leaf = c->leaf;
     o->state = (int)c->state; o->new_this_step = c->newThisTimeStep ? 1 : 0; o->color = -1;
     o->in_collection = c->internal ? 1 : 0;
+    o->hub_mask = 0; o->_pad = 0;
     auto st = [](double* d, const V3& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; };
     st(o->contactB1, c->contactB1); st(o->normalB1, c->normalB1); st(o->tangent1B1, c->tangent1B1); st(o->tangent2B1, c->tangent2B1);
     st(o->point_w, c->pointW); st(o->normal_w, c->normalW);

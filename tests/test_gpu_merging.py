@@ -35,3 +35,16 @@ def test_merge_then_unmerge_cascade():
 def test_mixed_scene_with_merging():
     gpu, cpu, ev_g, ev_o, worst = lockstep(mixed_scene(), params(), 200)
     assert ev_g == ev_o
+
+
+@pytest.mark.parametrize("scene", ["plate", "tower25platform"])
+def test_hub_mode_lockstep(scene):
+    """bodies touched by >= 8 body pairs (the plate / the sprung platform) are solved as hubs of the contact graph:
+    merging decisions must still match the oracle, which replays the hub sequence"""
+    from tests.util import golden_scene, hub_scene
+    from adaptivemerging_b200.ctypes_defs import apply_overrides
+    blob = hub_scene() if scene == "plate" else golden_scene("tower25platform")
+    p = apply_overrides(params(), blob.overrides)
+    gpu, cpu, ev_g, ev_o, worst = lockstep(blob, p, 150, tol=1e-6, options={"hub_min_degree": 8})
+    assert gpu.hub_contacts > 0
+    assert ev_g == ev_o

@@ -40,9 +40,14 @@ def test_contact_sets_bit_exact_teacher_forced(scene):
     assert checked > 50
 
 
-def test_pgs_bit_exact_in_colour_order():
+@pytest.mark.parametrize("hub_min", [64, 2])
+def test_pgs_bit_exact_in_colour_order(hub_min):
+    """hub_min = 2 forces the hub path (bodies touched by >= 2 body pairs are solved Jacobi-style across a colour,
+    DESIGN.md section 4); the oracle replays that sequence too"""
     blob = small_pile(4, 5, 4)
     gpu, cpu = _pair(blob, enable_merging=0)
+    gpu.set_option("hub_min_degree", hub_min)
+    gpu.record_orders(True)
     for _ in range(25):
         cpu.step(0.05)
     b = cpu.bodies()
@@ -50,9 +55,10 @@ def test_pgs_bit_exact_in_colour_order():
     assert gpu.detect() == cpu.detect() > 0
     gpu.solve(0.05)
     cg = gpu.contacts()
-    order = gpu.solve_order()
+    order = gpu.order(0)
+    assert (order["hub_mask"] != 0).any() == (hub_min == 2)
     cpu.apply_external_forces()
-    mism = cpu.solve(0.05, cg[order])
+    mism = cpu.solve(0.05, order)
     assert mism == 0
     co = cpu.contacts()
     ko = key_index(co)

@@ -71,13 +71,16 @@ def pile_with_bullet(nx=2, ny=3, nz=2, height=45.0):
     return _boxes_blob(np.ones((len(xs), 3)), xs, Rs)
 
 
-def lockstep(blob, p, steps, poke=None, tol=1e-6):
+def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
     from adaptivemerging_b200.system import RigidBodySystem
     from oracle.oracle import Oracle
     gpu = RigidBodySystem(0).load(blob, p)
     cpu = Oracle(blob, p)
     gpu.record_orders(True)
+    for k, v in (options or {}).items():
+        gpu.set_option(k, v)
     worst = 0.0
+    gpu.hub_contacts = 0
     for step in range(steps):
         if poke and step in poke:
             body, dv, dw = poke[step]
@@ -85,6 +88,7 @@ def lockstep(blob, p, steps, poke=None, tol=1e-6):
             cpu.add_body_velocity(body, dv, dw)
         gpu.advanceTime(0.05)
         full, sweep = gpu.order(0), gpu.order(1)
+        gpu.hub_contacts += int((full["hub_mask"] != 0).sum()) + int((sweep["hub_mask"] != 0).sum())
         cpu.set_next_orders(full=full if len(full) else None, sweep=sweep if len(sweep) else None)
         mism = cpu.step(0.05)
         assert mism == 0, f"step {step}: contact lists diverged ({mism} mismatches)"
@@ -127,3 +131,19 @@ def golden_scene(name):
 def golden_oracle(name):
     import os
     return np.load(os.path.join(GOLDEN, f"oracle_{name}.npz"))
+
+
+def hub_scene():
+    """a heavy unpinned plate on the plane carrying a 4x4 grid of small two-box towers: the plate is a hub of the
+    contact graph (16 body pairs), the small boxes are not"""
+    sb = SceneBuilder()
+    sb.add_plane((0, 0, 0), (0, 1, 0))
+    sb.add_box((8, 1, 8), (0, 0.5, 0), name="plate")
+    k = 0
+    for i in range(4):
+        for j in range(4):
+            x, z = -3 + 2 * i, -3 + 2 * j
+            sb.add_box((1, 1, 1), (x, 1.5, z), axis_angle=(0, 1, 0, 0.1 * k), name=f"a{k}")
+            sb.add_box((0.8, 0.8, 0.8), (x + 0.05, 2.4, z - 0.05), name=f"b{k}")
+            k += 1
+    return sb.build()

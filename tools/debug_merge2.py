@@ -10,6 +10,8 @@ blob = pile_with_bullet() if len(sys.argv) > 2 else small_pile()
 p = params()
 gpu = RigidBodySystem(0).load(blob, p); cpu = Oracle(blob, p)
 gpu.record_orders(True)
+import os
+if os.environ.get('HUB'): gpu.set_option('hub_min_degree', int(os.environ['HUB']))
 for step in range(int(sys.argv[1]) if len(sys.argv) > 1 else 14):
     gpu.advanceTime(0.05)
     full, sweep = gpu.order(0), gpu.order(1)
@@ -25,6 +27,15 @@ for step in range(int(sys.argv[1]) if len(sys.argv) > 1 else 14):
         gi = sorted((min(a, b), max(a, b), n, m) for a, b, n, m in zip(ib["body1"].tolist(), ib["body2"].tolist(), ib["n_contacts"].tolist(), ib["n_metric"].tolist()))
         oi = sorted((min(a, b), max(a, b), n, m) for a, b, n, m in zip(ob["body1"].tolist(), ob["body2"].tolist(), ob["n_contacts"].tolist(), ob["n_metric"].tolist()))
         print("  internal gpu", gi); print("  internal cpu", oi)
+    if max(errs.values()) > 1e-9 and not mism:
+        cg, co = gpu.contacts(), cpu.contacts()
+        from tests.util import key_index
+        ko = key_index(co)
+        io = np.array([ko[k][0] for k in map(tuple, contact_keys(cg).tolist())])
+        dl = np.abs(cg["lambda"] - co["lambda"][io]).max(1)
+        print(" lambda max diff", dl.max(), "at", int(dl.argmax()), cg[int(dl.argmax())][["body1","body2","info"]], "warm diff", np.abs(cg["lambda_warm"] - co["lambda_warm"][io]).max(),
+              "iters", tg.pgs_iterations, to.pgs_iterations, "hub contacts", int((full["hub_mask"] != 0).sum()), "colors", tg.pgs_colors)
+        break
     if mism:
         kg = set(map(tuple, contact_keys(gpu.contacts(True)).tolist()))
         ko = set(map(tuple, contact_keys(cpu.contacts(True)).tolist()))
