@@ -186,6 +186,8 @@ struct am3d_ctx {
   DevBuf<double> pokeV, pokeW;
   DevBuf<unsigned long long> tailKey, tailKeySorted;
   DevBuf<int> tailVal, tailIdx;
+  DevBuf<unsigned long long> wsKa, wsKb, wsK0s, wsK1s;  // (key0,key1)-sorted index of last step's contacts
+  DevBuf<int> wsIa, wsIb, wsIdx;
   DevBuf<double> B2CR, B2Ct;  // RigidBody.transformB2C of the leaves
   DevBuf<int> collCount, collStart, members, memVal, changedList, collMode, collFlagAcc, freeList;
   DevBuf<unsigned int> memKey, memKeySorted;

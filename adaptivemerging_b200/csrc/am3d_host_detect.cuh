@@ -110,10 +110,27 @@ static void warmStart(am3d_ctx* c) {
       return cub::DeviceRadixSort::SortPairs(t, b, c->tailKey.p, c->tailKeySorted.p, c->tailVal.p, c->tailIdx.p, nt, 0, 64, c->stream);
     });
   }
+  int ns = c->prev.nSorted;
+  int useIdx = c->NN > 0 && ns > 0;
+  if (useIdx) {  // stable sort of the canonical entries by key1, then by key0
+    c->wsKa.ensure(ns + 1); c->wsKb.ensure(ns + 1); c->wsK0s.ensure(ns + 1); c->wsK1s.ensure(ns + 1);
+    c->wsIa.ensure(ns + 1); c->wsIb.ensure(ns + 1); c->wsIdx.ensure(ns + 1);
+    LAUNCH(c, k_iota, nblk(ns), BLK, ns, c->wsIa.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->prev.key1.p, c->wsKa.p, c->wsIa.p, c->wsIb.p, ns, 0, 64, c->stream);
+    });
+    LAUNCH(c, k_gather_u64, nblk(ns), BLK, ns, c->wsIb.p, c->prev.key0.p, c->wsKb.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->wsKb.p, c->wsK0s.p, c->wsIb.p, c->wsIdx.p, ns, 0, 64, c->stream);
+    });
+    LAUNCH(c, k_gather_u64, nblk(ns), BLK, ns, c->wsIdx.p, c->prev.key1.p, c->wsK1s.p);
+  }
   WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,
             c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
             c->prev.n, c->prev.nSorted, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, c->prev.viol.p, c->prev.lam.p,
+            useIdx, c->wsK0s.p, c->wsK1s.p, c->wsIdx.p,
             c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
+  LAUNCH(c, k_warm_start_plain, nblk(c->cur.n), BLK, c->cur.n, W);
   LAUNCH(c, k_warm_start, nblk(nbp, 128), 128, nbp, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p, W);
 }
 

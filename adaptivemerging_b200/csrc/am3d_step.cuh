@@ -203,6 +203,10 @@ struct WarmCtx {
   const int *pb1, *pleaf;
   const double *ppB1, *pviol;
   double* plam;
+  // optional (key0,key1)-sorted index of the canonical entries (scenes with sphere trees: a pair can hold 10^4+ contacts)
+  int useIdx;
+  const unsigned long long *sk0, *sk1;
+  const int* sidx;
   // bodies / shapes
   const int *btype, *shType;
   const double *x, *R;
@@ -213,11 +217,26 @@ struct WarmCtx {
 // the reference's HashMap keeps the LAST one put, i.e. the last in DFS emission order = largest node rank
 __device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsigned long long k0, unsigned long long k1) {
   int best = -1, bestRank = -1;
-  for (int j = lo; j < hi; j++) {
-    if (W.pkey1[j] == k1) {
+  if (W.useIdx) {
+    int l = 0, h = W.npSorted;
+    while (l < h) {
+      int mid = (l + h) >> 1;
+      unsigned long long a = W.sk0[mid];
+      if (a < k0 || (a == k0 && W.sk1[mid] < k1)) l = mid + 1; else h = mid;
+    }
+    for (int t = l; t < W.npSorted && W.sk0[t] == k0 && W.sk1[t] == k1; t++) {  // equal keys stay in list order
+      int j = W.sidx[t];
       int lf = W.pleaf[j];
       int rk = lf >= 0 ? W.ndRank[lf] : 0;
       if (best < 0 || rk > bestRank) { best = j; bestRank = rk; }
+    }
+  } else {
+    for (int j = lo; j < hi; j++) {
+      if (W.pkey1[j] == k1) {
+        int lf = W.pleaf[j];
+        int rk = lf >= 0 ? W.ndRank[lf] : 0;
+        if (best < 0 || rk > bestRank) { best = j; bestRank = rk; }
+      }
     }
   }
   int nt = W.np - W.npSorted;
@@ -248,6 +267,39 @@ __device__ __forceinline__ d3 worldPoint(const double* x, const double* R, int b
   return xfP(T, pB);
 }
 
+// range of previous contacts with the same (bodyLo, bodyHi, partLo, partHi)
+__device__ __forceinline__ void warmRange(const WarmCtx& W, unsigned long long k0, int& rlo, int& rhi) {
+  rlo = rhi = 0;
+  if (W.useIdx) return;
+  int lo = 0, hi = W.npSorted;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] < k0) lo = mid + 1; else hi = mid; }
+  rlo = lo;
+  hi = W.npSorted;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] <= k0) lo = mid + 1; else hi = mid; }
+  rhi = lo;
+}
+
+// pairs without a box-box part (CollisionProcessor.java:479-495): plain key lookup, nothing is taken away from the
+// donor, so the contacts of a pair are independent -> one thread per contact
+__global__ void k_warm_start_plain(int nc, WarmCtx W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  int t1 = W.btype[W.b1[i]], t2 = W.btype[W.b2[i]];
+  bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
+  if (boxy) return;
+  unsigned long long k0 = W.key0[i], k1 = W.key1[i];
+  int rlo, rhi;
+  warmRange(W, k0, rlo, rhi);
+  int j = warmLookup(W, rlo, rhi, k0, k1);
+  if (j >= 0) warmTake(W, i, j, false); else W.isNew[i] = 1;
+}
+
+__global__ void k_gather_u64(int n, const int* __restrict__ idx, const unsigned long long* __restrict__ src,
+                             unsigned long long* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+
 __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int* __restrict__ bcount,
                              const int* __restrict__ bb1, const int* __restrict__ bb2, WarmCtx W) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,15 +307,11 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
   int s = bstart[b], e = s + bcount[b];
   int t1 = W.btype[bb1[b]], t2 = W.btype[bb2[b]];
   bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
+  if (!boxy) return;  // k_warm_start_plain
   for (int i = s; i < e; i++) {
     unsigned long long k0 = W.key0[i], k1 = W.key1[i];
-    // range of previous contacts with the same (bodyLo, bodyHi, partLo, partHi)
-    int lo = 0, hi = W.npSorted;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] < k0) lo = mid + 1; else hi = mid; }
-    int rlo = lo;
-    hi = W.npSorted;
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] <= k0) lo = mid + 1; else hi = mid; }
-    int rhi = lo;
+    int rlo, rhi;
+    warmRange(W, k0, rlo, rhi);
     bool vanillaOnly = !boxy;
     bool doBox = boxy;
     if (boxy) {

@@ -5,7 +5,7 @@ import bench
 from adaptivemerging_b200.system import RigidBodySystem
 name = sys.argv[1]; size = int(sys.argv[2]); steps = int(sys.argv[3]); merging = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 every = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-blob, p, desc = bench.build_workload(name, size, merging)
+blob, p, desc = bench.build_workload(name, size, merging, float(os.environ['Y0']) if os.environ.get('Y0') else None)
 s = RigidBodySystem(0).load(blob, p)
 import time
 for i in range(steps):
