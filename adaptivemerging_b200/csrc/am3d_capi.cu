@@ -292,7 +292,10 @@ int am3d_create(int device, am3d_ctx** out) {
     int coop = 0, sms = 0, perSm = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent, 128, 0));
+    if (const char* e = getenv("AM3D_PGS_MINB")) c->pgsMinB = atoi(e);
+    if (c->pgsMinB >= 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<4>, 128, 0));
+    else if (c->pgsMinB == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<3>, 128, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<1>, 128, 0));
     c->coopBlocks = coop ? sms * perSm : 0;
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
@@ -560,7 +563,7 @@ int am3d_set_lambdas(am3d_ctx* c, const double* lam, int count) {
 
 int am3d_download_deltav(am3d_ctx* c, double* dv) {
   API_BEGIN(c)
-  CK(cudaMemcpyAsync(dv, c->dv.p, 6 * (size_t)c->NB * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpy2DAsync(dv, 6 * sizeof(double), c->dv.p, DVS * sizeof(double), 6 * sizeof(double), c->NB, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   API_END(c)
 }

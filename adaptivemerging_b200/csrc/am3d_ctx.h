@@ -5,6 +5,7 @@
 // live in a "solver body" index space [0,NB) = leaf bodies in XML parse order, [NB, NB+NCcap) =
 // RigidCollection slots, so that the PGS kernels address a merged collection exactly like a free body.
 #pragma once
+#define DVS 8  // deltaV stride in doubles: 6 used, padded so that a body is two aligned 32-byte accesses
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -228,6 +229,7 @@ struct am3d_ctx {
   cudaEvent_t ev[16];
   bool evCreated = false;
   int coopBlocks = 0;     // co-resident CTAs for the cooperative PGS kernel (0: cooperative launch unsupported)
+  int pgsMinB = 1;        // __launch_bounds__ min blocks per SM of the PGS kernels (register cap; AM3D_PGS_MINB)
   int usePersistent = 1;  // 0 never, 1 heuristic, 2 always (AM3D_PGS_PERSISTENT)
   long long solveLaunches = 0;
   long long kernelLaunches = 0;

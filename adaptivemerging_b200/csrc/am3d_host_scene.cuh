@@ -78,8 +78,8 @@ static void resetState(am3d_ctx* c) {
     }
   }
   h2dv(c, c->jinv, jinv); h2dv(c, c->mA, mA);
-  c->force.ensure(3 * NS); c->torque.ensure(3 * NS); c->dv.ensure(6 * NS);
-  c->force.zero(3 * NS, c->stream); c->torque.zero(3 * NS, c->stream); c->dv.zero(6 * NS, c->stream);
+  c->force.ensure(3 * NS); c->torque.ensure(3 * NS); c->dv.ensure(DVS * (size_t)NS + 8);
+  c->force.zero(3 * NS, c->stream); c->torque.zero(3 * NS, c->stream); c->dv.zero(DVS * (size_t)NS, c->stream);
   c->metricHist.ensure(10 * NS); c->metricHist.zero(10 * NS, c->stream);
   c->metricCount.ensure(NS); c->metricCount.zero(NS, c->stream);
   c->hasExt.ensure(NS); c->hasExt.zero(NS, c->stream);

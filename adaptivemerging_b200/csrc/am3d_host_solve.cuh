@@ -15,7 +15,7 @@ static ContactPtrs contactPtrs(ContactSet& S) {
 }
 
 // colour the groups (body pairs) so that no two groups of a colour share a non-pinned solver body
-static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, int inCollection) {
+static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, int inCollection) {
   c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
   c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
   c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
@@ -51,8 +51,8 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, in
   int maxColors = (page + 1) * 64;
   c->colorHist.ensure(maxColors + 1);
   CK(cudaMemsetAsync(c->colorHist.p, 0, (maxColors + 1) * sizeof(int), c->stream));
-  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, c->grpKey.p, c->grpVal.p, c->colorHist.p);
-  int endBit = 32 + bitsFor((unsigned long long)maxColors);
+  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, c->grpKey.p, c->grpVal.p, c->colorHist.p);
+  int endBit = 8 + bitsFor((unsigned long long)maxColors);
   cubRun(c, [&](void* t, size_t& b) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
   });
@@ -101,7 +101,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
          c->icon.b1.p, c->icon.b2.p, c->ibp.count.p, c->ibp.start.p, c->ibp.alive.p, c->parent.p, c->flags.p, c->swB1.p, c->swB2.p,
          c->swCount.p, c->swStart.p);
   gb1 = c->swB1.p; gb2 = c->swB2.p; gcount = c->swCount.p; gstart = c->swStart.p;
-  colourGroups(c, ng, gb1, gb2, sweep ? 1 : 0);
+  colourGroups(c, ng, gb1, gb2, gcount, sweep ? 1 : 0);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
   c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1);
   c->scP.ensure(24 * (size_t)nc + 48); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1); c->hubDelta.ensure(12 * (size_t)ng + 12);
@@ -173,13 +173,14 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     double* dvp = c->dv.p;
     unsigned long long* isp = c->iterState.p;
     void* args[] = {&nColors, &dcs, &dcr, &HR, &S, &dvp, &PP, &iterations, &chk, &isp};
-    CK(cudaLaunchCooperativeKernel((void*)k_pgs_persistent, dim3(c->coopBlocks), dim3(128), args, 0, c->stream));
+    const void* kfn = c->pgsMinB >= 4 ? (const void*)k_pgs_persistent<4> : c->pgsMinB == 3 ? (const void*)k_pgs_persistent<3> : (const void*)k_pgs_persistent<1>;
+    CK(cudaLaunchCooperativeKernel(kfn, dim3(c->coopBlocks), dim3(128), args, 0, c->stream));
     c->kernelLaunches++;
-    c->solveLaunches++;
+    if (!sweep) c->solveLaunches++;
   } else {
     for (int k = 0; k < c->nColors; k++) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-      LAUNCH(c, k_pgs_color<0>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+      LAUNCH(c, (k_pgs_color<0, 1>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
       int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
       if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 0);
     }
@@ -187,10 +188,12 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
       int last = it == iterations - 1;
       for (int k = 0; k < c->nColors; k++) {
         int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-        LAUNCH(c, k_pgs_color<1>, nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        if (c->pgsMinB >= 4) LAUNCH(c, (k_pgs_color<1, 4>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        else if (c->pgsMinB == 3) LAUNCH(c, (k_pgs_color<1, 3>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        else LAUNCH(c, (k_pgs_color<1, 1>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
         if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 1);
-        c->solveLaunches++;
+        if (!sweep) c->solveLaunches++;
       }
       LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);
     }

@@ -229,3 +229,16 @@ AMD xf xfAinvB(const xf& A, const xf& B) {
   r.R = mmul(Rt, B.R);
   return r;
 }
+
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256).  The sweep is bound by the number of scattered memory
+// instructions per group, not by bytes: one 32-byte access per thread costs the load/store unit what an 8-byte one does.
+__device__ __forceinline__ void ld4(const double* p, double* o) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void ld4cg(const double* p, double* o) {  // L2 only: written by other SMs between colours
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+

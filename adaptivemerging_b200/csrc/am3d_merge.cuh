@@ -536,7 +536,7 @@ __global__ void k_unm_apply(int nb, int* __restrict__ parent, const int* __restr
   d3 om = ld3(w + 3 * p);
   st3(v + 3 * i, vadd(ld3(v + 3 * p), vcross(om, rr)));
   st3(w + 3 * i, om);
-  for (int k = 0; k < 6; k++) dv[6 * i + k] = 0;
+  for (int k = 0; k < DVS; k++) dv[DVS * (size_t)i + k] = 0;
   if (needNew[r]) {
     int slot = freeList[newScan[r]];
     parent[i] = nb + slot;
@@ -673,16 +673,16 @@ __global__ void k_sweep_finish(int ns, int nb, const int* __restrict__ parent, c
     int p = parent[i];
     if (p >= 0 && !(flags[p] & AM3D_F_SLEEPING) && !(flags[i] & AM3D_F_PINNED)) {
       d3 vv = vscaleAdd(dt * minv[i], ld3(force + 3 * i), ld3(v + 3 * i));
-      vv = vadd(vv, ld3(dv + 6 * i));
+      vv = vadd(vv, ld3(dv + DVS * (size_t)i));
       d3 dom = mtransform(ldm(jinv + 9 * i), ld3(torque + 3 * i));
       dom = vscale(dt, dom);
       d3 ww = vadd(ld3(w + 3 * i), dom);
-      ww = vadd(ww, ld3(dv + 6 * i + 3));
+      ww = vadd(ww, ld3(dv + DVS * (size_t)i + 3));
       st3(v + 3 * i, vv);
       st3(w + 3 * i, ww);
     }
   }
-  for (int k = 0; k < 6; k++) dv[6 * i + k] = 0;
+  for (int k = 0; k < DVS; k++) dv[DVS * (size_t)i + k] = 0;
 }
 // the re-clear + re-apply of external forces on top-level bodies once a merge event happened (:138-142)
 __global__ void k_reclear_top(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
@@ -695,7 +695,7 @@ __global__ void k_reclear_top(int ns, int nb, const int* __restrict__ alive, con
   if (useGravity) f = vadd(f, vscale(-mass[i], d3(gx, gy, 0)));
   st3(force + 3 * i, f);
   st3(torque + 3 * i, d3(0, 0, 0));
-  for (int k = 0; k < 6; k++) dv[6 * i + k] = 0;
+  for (int k = 0; k < DVS; k++) dv[DVS * (size_t)i + k] = 0;
 }
 // collections carry their members along (RigidCollection.updateBodiesPositionAndTransformations :898-909,
 // applyVelocitiesToBodies :914-918)

@@ -43,7 +43,7 @@ __global__ void k_clear_gravity(int ns, int nb, const int* __restrict__ alive, c
   st3(force + 3 * i, f);
   st3(torque + 3 * i, d3(0, 0, 0));
 #pragma unroll
-  for (int k = 0; k < 6; k++) dv[6 * i + k] = 0.0;
+  for (int k = 0; k < DVS; k++) dv[DVS * (size_t)i + k] = 0.0;
 }
 
 __device__ __forceinline__ d3 spatialVelocity(const double* x, const double* v, const double* w, int b, const d3& pW) {
@@ -563,11 +563,14 @@ __global__ void k_color_next_page(int ng, int page, int* __restrict__ color) {
   if (g >= ng) return;
   if (color[g] == -2 - page) color[g] = -1;
 }
-__global__ void k_color_sortkey(int ng, const int* __restrict__ color, unsigned long long* __restrict__ key,
-                                int* __restrict__ val, int* __restrict__ hist) {
+// solve order: by colour; inside a colour (any order gives the same result: the groups share no free body) by
+// descending contact count so that the lanes of a warp run the same number of contacts; ties by group index
+// (the radix sort is stable)
+__global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount,
+                                unsigned long long* __restrict__ key, int* __restrict__ val, int* __restrict__ hist) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
-  key[g] = ((unsigned long long)(unsigned)color[g] << 32) | (unsigned)g;
+  key[g] = ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
   val[g] = g;
   atomicAdd(hist + color[g], 1);
 }
@@ -667,7 +670,8 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
     p = ld3(pW + 3 * i); n = ld3(nW + 3 * i); t1 = ld3(t1W + 3 * i); t2 = ld3(t2W + 3 * i);
   }
   d3 r1 = vsub(p, ld3(x + 3 * a)), r2 = vsub(p, ld3(x + 3 * b));
-  double* PK = S.scP + 24 * (size_t)idx;
+  double* PKg = S.scP + 24 * (size_t)idx;
+  double PK[24];
   st3(PK, n); st3(PK + 3, t1); st3(PK + 6, t2);
   st3(PK + 9, r1); st3(PK + 12, r2);
   // Jacobian rows
@@ -714,6 +718,8 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
     PK[18 + k] = mi1 * vdot(jav, jav) + vdot(jaw[k], tmp1) + mi2 * vdot(dir[k], dir[k]) + vdot(jbw[k], tmp2);
     PK[21 + k] = lam[3 * i + k];
   }
+#pragma unroll
+  for (int k = 0; k < 6; k++) st4(PKg + 4 * k, PK[4 * k], PK[4 * k + 1], PK[4 * k + 2], PK[4 * k + 3]);
   S.scSrc[idx] = i | (setId << 30);
   S.scState[idx] = cstate[i];
 }
@@ -746,7 +752,6 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
 // A hub side works on a private copy of the hub's deltaV as of the start of the colour (plus this group's own
 // updates) and hands what it added to hubDelta; k_hub_reduce folds the deltas in after the colour, in a fixed order.
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 template <int MODE>
 __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
                                          double& localMax) {
@@ -755,27 +760,30 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   const double* PK0 = S.scP + 24 * (size_t)start;
   if (cnt > 0) { prefetchL2(PK0); prefetchL2(PK0 + 16); }
   double M[20];
-  const double* Mp = S.sgMass + 20 * p;
+  const double* Mp = S.sgMass + 20 * (size_t)p;
 #pragma unroll
-  for (int k = 0; k < 20; k++) M[k] = Mp[k];
+  for (int k = 0; k < 5; k++) ld4(Mp + 4 * k, M + 4 * k);
   double mu = S.sgMu[p];
   int fl = S.sgFlags[p];
   bool clamp = fl & SG_CLAMP;
   bool hubA = fl & SG_HUB1, hubB = fl & SG_HUB2;
-  double dv1[6], dv2[6], acc1[6], acc2[6];
+  double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
-  for (int k = 0; k < 6; k++) {
-    dv1[k] = a >= 0 ? __ldcg(dv + 6 * a + k) : 0.0;
-    dv2[k] = b >= 0 ? __ldcg(dv + 6 * b + k) : 0.0;
-    acc1[k] = 0.0;
-    acc2[k] = 0.0;
-  }
+  for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
+  if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
+  if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
+#pragma unroll
+  for (int k = 0; k < 6; k++) { acc1[k] = 0.0; acc2[k] = 0.0; }
   for (int c = 0; c < cnt; c++) {
     double* PK = S.scP + 24 * (size_t)(start + c);
     if (c + 1 < cnt) { prefetchL2(PK + 24); prefetchL2(PK + 40); }  // next contact: hide the load latency of the sequential chain
-    d3 dir[3] = {ld3(PK), ld3(PK + 3), ld3(PK + 6)};
-    d3 r1 = ld3(PK + 9), r2 = ld3(PK + 12);
-    double lam[3] = {PK[21], PK[22], PK[23]};
+    double Q[24];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ld4(PK + 4 * k, Q + 4 * k);
+    ld4cg(PK + 20, Q + 20);  // D[2] and lambda: rewritten every sweep
+    d3 dir[3] = {{Q[0], Q[1], Q[2]}, {Q[3], Q[4], Q[5]}, {Q[6], Q[7], Q[8]}};
+    d3 r1 = {Q[9], Q[10], Q[11]}, r2 = {Q[12], Q[13], Q[14]};
+    double lam[3] = {Q[21], Q[22], Q[23]};
     if (MODE == 0) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -786,8 +794,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
         if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, lam[k]);
       }
     } else {
-      double bb[3] = {PK[15], PK[16], PK[17]};
-      double DD[3] = {PK[18], PK[19], PK[20]};
+      double bb[3] = {Q[15], Q[16], Q[17]};
+      double DD[3] = {Q[18], Q[19], Q[20]};
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
@@ -810,7 +818,7 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
         if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, diff);
         localMax = fmax(localMax, fabs(diff));
       }
-      PK[21] = lam[0]; PK[22] = lam[1]; PK[23] = lam[2];
+      st4(PK + 20, DD[2], lam[0], lam[1], lam[2]);
       if (lastIter) {
         // Contact.updateContactState :385-398
         d3 jaw1 = vcross(dir[1], r1), jbw1 = vcross(r2, dir[1]);
@@ -828,8 +836,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (a >= 0) {
     if (!hubA) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+      st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
+      st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + k] = acc1[k];
@@ -837,8 +845,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (b >= 0) {
     if (!hubB) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+      st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
+      st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + 6 + k] = acc2[k];
@@ -869,7 +877,7 @@ __device__ __forceinline__ void hubReduceRun(int r, const HubRuns& H, const doub
   if (lane == 0) {
     int h = H.runBody[r];
 #pragma unroll
-    for (int k = 0; k < 6; k++) dv[6 * h + k] = __ldcg(dv + 6 * h + k) + s[k];
+    for (int k = 0; k < 6; k++) dv[DVS * (size_t)h + k] = __ldcg(dv + DVS * (size_t)h + k) + s[k];
   }
 }
 __global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __restrict__ hubDelta, double* __restrict__ dv,
@@ -879,8 +887,8 @@ __global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __re
   if (r < rEnd) hubReduceRun(r, H, hubDelta, dv);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
             unsigned long long* __restrict__ iterState) {
   if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
@@ -897,7 +905,8 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
 // The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
 // colour (two when the colour has hub runs).  Used when the colours are many and small (batched scenes): thousands
 // of tiny launches become grid syncs.  Same Gauss-Seidel sequence as the per-colour launches.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H,
                  SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance,
                  unsigned long long* __restrict__ iterState) {
@@ -1026,11 +1035,11 @@ __global__ void k_advance_velocities(int ns, int nb, const int* __restrict__ ali
   if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
   if (flags[i] & (AM3D_F_PINNED | AM3D_F_SLEEPING)) return;
   d3 vv = vscaleAdd(dt * minv[i], ld3(force + 3 * i), ld3(v + 3 * i));
-  vv = vadd(vv, ld3(dv + 6 * i));
+  vv = vadd(vv, ld3(dv + DVS * (size_t)i));
   d3 dom = mtransform(ldm(jinv + 9 * i), ld3(torque + 3 * i));
   dom = vscale(dt, dom);
   d3 ww = vadd(ld3(w + 3 * i), dom);
-  ww = vadd(ww, ld3(dv + 6 * i + 3));
+  ww = vadd(ww, ld3(dv + DVS * (size_t)i + 3));
   st3(v + 3 * i, vv);
   st3(w + 3 * i, ww);
 }

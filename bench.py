@@ -139,6 +139,18 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes (read + write) per contact per PGS iteration of the sweep kernel, from the committed
+    `ncu --set full` capture (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum divided by
+    the contact-iterations of the captured launches)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            d = json.load(f)[kernel]
+        return float(d["dram_bytes_per_contact_iter"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  No JVM exists on the box, so
     this is the single-threaded C++ restatement under oracle/ (kind = "port"), on a bounded sample."""
@@ -224,6 +236,9 @@ def main():
 
     # ---- resident-state leg -------------------------------------------------------------------
     s0 = sysm.stats()
+    profiling = bool(os.environ.get("AM3D_CUDA_PROFILER"))  # ncu --profile-from-start off: capture the timed region only
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     clocks = ClockSampler(local)
     clocks.start()
     barrier()
@@ -239,6 +254,8 @@ def main():
     ms = sysm.elapsed_ms()
     barrier()
     wall = time.perf_counter() - t0
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
     clk = clocks.stop()
     s1 = sysm.stats()
     tm = sysm.timings()
@@ -265,7 +282,7 @@ def main():
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
     counts = torch.tensor([float(nb), float(s1["row_updates"] - s0["row_updates"]), float(s1["solve_seconds"] - s0["solve_seconds"]),
-                           float(s1["kernel_launches"] - s0["kernel_launches"])], dtype=torch.float64, device=f"cuda:{local}")
+                           float(s1["kernel_launches"] - s0["kernel_launches"]), float(s1["solve_launches"] - s0["solve_launches"])], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         tot = counts.clone()
@@ -285,6 +302,11 @@ def main():
     solve_s = float(counts[2])
     peak, peak_src = hbm_peak()
     achieved = (row_updates / 3.0) * PGS_BYTES_PER_CONTACT_ITER / max(solve_s, 1e-12) / 1e9
+    solve_launches = max(float(counts[4]), 1.0)
+    persistent = solve_launches <= 2 * args.steps  # one cooperative launch per solve vs one launch per colour per iteration
+    kernel = "k_pgs_persistent" if persistent else "k_pgs_color<1>"
+    traffic_ratio, traffic_src = measured_traffic(kernel)
+    contact_iters_per_launch = (row_updates / 3.0) / solve_launches
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -302,9 +324,13 @@ def main():
         "phase_ms_last_step": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "lcp_solve": tm.lcp_solve * 1e3,
                                "pgs_sweeps": tm.pgs_kernel_time * 1e3, "post": tm.merging * 1e3, "total": tm.compute_time * 1e3},
         "wall_ms_per_step": 1e3 * wall / args.steps,
-        "roofline": {"bound": "hbm", "kernel": "k_pgs_color<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes": "752 B per contact per PGS iteration"},
+        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak,
+                     "traffic": None if traffic_ratio is None else traffic_ratio * contact_iters_per_launch,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes": "752 B per contact per PGS iteration (SURVEY.md 8d)",
+                     "algorithmic_bytes_per_launch": PGS_BYTES_PER_CONTACT_ITER * contact_iters_per_launch,
+                     "launches": int(solve_launches), "avg_launch_ms": 1e3 * solve_s / solve_launches},
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle.oracle import Oracle
