@@ -210,6 +210,8 @@ static void stepOnce(am3d_ctx* c, double dt) {
   CK(cudaEventRecord(c->ev[7], c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->T.detection = evMs(c, 1, 2) * 1e-3;
+  c->T.narrowphase_kernel_time = c->narrowTimed ? (evMs(c, 16, 17) + evMs(c, 18, 19)) * 1e-3 : 0.0;
+  c->narrowTimed = false;
   c->T.warmstart = evMs(c, 2, 3) * 1e-3;
   c->T.update_collections = swept ? evMs(c, 3, 14) * 1e-3 : 0;
   c->T.single_it_pgs = swept ? evMs(c, 8, 9) * 1e-3 : 0;
@@ -286,7 +288,7 @@ int am3d_create(int device, am3d_ctx** out) {
   try {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; i++) CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 20; i++) CK(cudaEventCreate(&c->ev[i]));
     c->evCreated = true;
     am3d_default_params(&c->P);
     int coop = 0, sms = 0, perSm = 0;
@@ -310,7 +312,7 @@ int am3d_destroy(am3d_ctx* c) {
   if (!c) return AM3D_EINVAL;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->evCreated) for (int i = 0; i < 16; i++) cudaEventDestroy(c->ev[i]);
+  if (c->evCreated) for (int i = 0; i < 20; i++) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return AM3D_OK;

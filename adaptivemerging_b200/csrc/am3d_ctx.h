@@ -226,7 +226,8 @@ struct am3d_ctx {
 
   // ---- timing --------------------------------------------------------------------------------------
   am3d_timings T;
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[20];
+  bool narrowTimed = false;  // events 16..19 were recorded by the last detect()
   bool evCreated = false;
   int coopBlocks = 0;     // co-resident CTAs for the cooperative PGS kernel (0: cooperative launch unsupported)
   int pgsMinB = 1;        // __launch_bounds__ min blocks per SM of the PGS kernels (register cap; AM3D_PGS_MINB)

@@ -50,20 +50,25 @@ static void detect(am3d_ctx* c) {
     HitOut HO{c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p};
     bool haveTrees = c->NN > 0;
     CK(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev[16], c->stream));
     if (haveTrees)
       LAUNCH(c, k_narrow_tree<false>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
              c->pairSlot.p, TC, HO, c->pairCap.p, c->counters.p + 1);
+    CK(cudaEventRecord(c->ev[17], c->stream));
     int nslots = scanTotal(c, c->pairCap, c->pairSlot, np);
     c->nSlots = nslots;
     c->hitPos.ensure(3 * (size_t)nslots + 3); c->hitNrm.ensure(3 * (size_t)nslots + 3); c->hitViol.ensure((size_t)nslots + 1);
     c->hitMeta.ensure(4 * (size_t)nslots + 4);
     HO = HitOut{c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p};
     CK(cudaMemsetAsync(c->pairCount.p, 0, (np + 1) * sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev[18], c->stream));
     LAUNCH(c, k_narrow_box, nblk(np, 128), 128, np, c->pairValSorted.p, c->pairType.p, c->pairSlot.p, c->shSize.p, c->shRadius.p,
            c->shX.p, c->shR.p, HO, c->pairCount.p);
     if (haveTrees)
       LAUNCH(c, k_narrow_tree<true>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
              c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1);
+    CK(cudaEventRecord(c->ev[19], c->stream));
+    c->narrowTimed = true;
     nc = scanTotal(c, c->pairCount, c->pairOut, np);
     if (haveTrees && readInt(c, c->counters.p + 1)) throw AmError(AM3D_ECAPACITY, "sphere-tree traversal stack overflow");
     c->cur.ensure(nc + 1);

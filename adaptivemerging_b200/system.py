@@ -116,8 +116,14 @@ class RigidBodySystem:
     def n_bodies(self):
         return self._L.am3d_num_bodies(self._h)
 
-    def bodies(self):
+    def bodies(self, out=None):
+        """Body state of the leaf bodies.  `out`: a dict returned by an earlier call (or caller-owned, e.g. pinned,
+        arrays of the same shapes) to download into without allocating."""
         n = self.n_bodies
+        if out is not None:
+            x, R, v, w, sl, co = out["x"], out["R"], out["v"], out["omega"], out["sleeping"], out["collection"]
+            self._ck(self._L.am3d_download_bodies(self._h, _p(x), _p(R), _p(v), _p(w), _p(sl), _p(co)))
+            return out
         x = np.empty((n, 3)); R = np.empty((n, 9)); v = np.empty((n, 3)); w = np.empty((n, 3))
         sl = np.empty(n, np.int32); co = np.empty(n, np.int32)
         self._ck(self._L.am3d_download_bodies(self._h, _p(x), _p(R), _p(v), _p(w), _p(sl), _p(co)))

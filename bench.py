@@ -245,11 +245,15 @@ def main():
     sysm.mark(0)
     t0 = time.perf_counter()
     contacts = iters = 0
+    np_bytes = np_s = 0.0
     for _ in range(args.steps):
         sysm.advanceTime(0.05)
         t = sysm.timings()
         contacts += t.n_contacts
         iters += t.pgs_iterations
+        # narrowphase, SURVEY.md 8d: 8 B + 2 x 96 B per candidate pair, 80 B per emitted contact
+        np_bytes += 200.0 * t.n_pairs + 80.0 * t.n_contacts
+        np_s += t.narrowphase_kernel_time
     sysm.mark(1)
     ms = sysm.elapsed_ms()
     barrier()
@@ -268,17 +272,20 @@ def main():
     poke_w = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
     pv, pw = poke_v.numpy(), poke_w.numpy()
     h2d = pv.nbytes + pw.nbytes
+    pinned = {"x": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "R": torch.empty((n, 9), dtype=torch.float64).pin_memory(),
+              "v": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "omega": torch.empty((n, 3), dtype=torch.float64).pin_memory(),
+              "sleeping": torch.empty(n, dtype=torch.int32).pin_memory(), "collection": torch.empty(n, dtype=torch.int32).pin_memory()}
+    state = {k: t.numpy() for k, t in pinned.items()}
     d2h = n * (3 + 9 + 3 + 3) * 8 + 2 * 4 * n
     barrier()
     sysm.mark(0)
     for _ in range(args.steps):
         sysm.add_velocities(pv, pw)
         sysm.advanceTime(0.05)
-        state = sysm.bodies()
+        sysm.bodies(out=state)
     sysm.mark(1)
     ms_e2e = sysm.elapsed_ms()
     barrier()
-    del state
 
     times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
     counts = torch.tensor([float(nb), float(s1["row_updates"] - s0["row_updates"]), float(s1["solve_seconds"] - s0["solve_seconds"]),
@@ -331,6 +338,10 @@ def main():
                      "algorithmic_bytes": "752 B per contact per PGS iteration (SURVEY.md 8d)",
                      "algorithmic_bytes_per_launch": PGS_BYTES_PER_CONTACT_ITER * contact_iters_per_launch,
                      "launches": int(solve_launches), "avg_launch_ms": 1e3 * solve_s / solve_launches},
+        "roofline_narrowphase": {"bound": "hbm", "kernel": "k_narrow_box + k_narrow_tree<0/1>", "achieved": np_bytes / max(np_s, 1e-12) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "frac": np_bytes / max(np_s, 1e-12) / 1e9 / peak,
+                                 "algorithmic_bytes": "200 B per candidate pair + 80 B per contact (SURVEY.md 8d)",
+                                 "ms_per_step": 1e3 * np_s / args.steps},
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle.oracle import Oracle

@@ -220,6 +220,7 @@ typedef struct am3d_timings {
   int32_t n_pairs;        /* broadphase candidate pairs */
   int32_t n_collections;
   double pgs_kernel_time; /* device time of the full-solve sweeps only */
+  double narrowphase_kernel_time; /* device time of the narrowphase kernels (count + emit passes) */
 } am3d_timings;
 
 /* One contact as the tests and the Java mirror see it (Contact.java fields). */
