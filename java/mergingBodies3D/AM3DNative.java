@@ -1,0 +1,109 @@
+package mergingBodies3D;
+
+import java.lang.foreign.Arena;
+import java.lang.foreign.FunctionDescriptor;
+import java.lang.foreign.Linker;
+import java.lang.foreign.MemorySegment;
+import java.lang.foreign.SymbolLookup;
+import java.lang.invoke.MethodHandle;
+
+import static java.lang.foreign.ValueLayout.ADDRESS;
+import static java.lang.foreign.ValueLayout.JAVA_DOUBLE;
+import static java.lang.foreign.ValueLayout.JAVA_INT;
+
+/**
+ * Panama FFM binding of libam3d.so (include/am3d.h).  One instance = one am3d_ctx = one GPU.
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S BUILD IMAGE (no JDK there); needs JDK >= 22 (java.lang.foreign is final).
+ * It lives in package mergingBodies3D so that it can read the package-private fields of the reference classes.
+ * Every handle below binds one declaration of include/am3d.h; the Python ctypes binding used by the tests
+ * (adaptivemerging_b200/_capi.py) makes the same calls.
+ */
+final class AM3DNative implements AutoCloseable {
+    private static final Linker L = Linker.nativeLinker();
+    private static final SymbolLookup LIB =
+            SymbolLookup.libraryLookup(System.getProperty("am3d.library", "libam3d.so"), Arena.global());
+
+    private static MethodHandle h(String name, FunctionDescriptor d) {
+        return L.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), d);
+    }
+
+    private static final MethodHandle CREATE = h("am3d_create", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle DESTROY = h("am3d_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle LAST_ERROR = h("am3d_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
+    private static final MethodHandle DEFAULT_PARAMS = h("am3d_default_params", FunctionDescriptor.ofVoid(ADDRESS));
+    private static final MethodHandle UPLOAD_SCENE = h("am3d_upload_scene", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_PARAMS = h("am3d_set_params", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle RESET = h("am3d_reset", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle STEP = h("am3d_step", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT));
+    private static final MethodHandle NUM_BODIES = h("am3d_num_bodies", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle DOWNLOAD_BODIES = h("am3d_download_bodies",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle NUM_CONTACTS = h("am3d_num_contacts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle DOWNLOAD_CONTACTS = h("am3d_download_contacts",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
+    private static final MethodHandle GET_TIMINGS = h("am3d_get_timings", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle SET_BODY_VELOCITY = h("am3d_set_body_velocity",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle ADD_BODY_VELOCITY = h("am3d_add_body_velocity",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle ADD_VELOCITIES = h("am3d_add_velocities", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+
+    /** sizeof(am3d_params), sizeof(am3d_timings), sizeof(am3d_contact): see the struct definitions in am3d.h */
+    static final long SIZEOF_PARAMS = 264, SIZEOF_TIMINGS = 128, SIZEOF_CONTACT = 264;
+
+    final Arena arena = Arena.ofShared();
+    private final MemorySegment ctx;
+
+    AM3DNative(int device) {
+        MemorySegment out = arena.allocate(ADDRESS);
+        // AM3D_ENOGPU (-3) when there is no CUDA device: the library has no CPU fallback
+        int rc;
+        try { rc = (int) CREATE.invokeExact(device, out); } catch (Throwable t) { throw new RuntimeException(t); }
+        if (rc != 0) throw new IllegalStateException("am3d_create failed: " + rc);
+        ctx = out.get(ADDRESS, 0);
+    }
+
+    private void check(int rc) {
+        if (rc == 0) return;
+        String msg;
+        try {
+            MemorySegment s = (MemorySegment) LAST_ERROR.invokeExact(ctx);
+            msg = s.reinterpret(4096).getString(0);
+        } catch (Throwable t) { msg = "?"; }
+        throw new IllegalStateException("am3d error " + rc + ": " + msg);
+    }
+
+    MemorySegment defaultParams() {
+        MemorySegment p = arena.allocate(SIZEOF_PARAMS, 8);
+        try { DEFAULT_PARAMS.invokeExact(p); } catch (Throwable t) { throw new RuntimeException(t); }
+        return p;
+    }
+    void uploadScene(MemorySegment am3dScene) { try { check((int) UPLOAD_SCENE.invokeExact(ctx, am3dScene)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void setParams(MemorySegment am3dParams) { try { check((int) SET_PARAMS.invokeExact(ctx, am3dParams)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void reset() { try { check((int) RESET.invokeExact(ctx)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void step(double dt, int n) { try { check((int) STEP.invokeExact(ctx, dt, n)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    int numBodies() { try { return (int) NUM_BODIES.invokeExact(ctx); } catch (Throwable t) { throw new RuntimeException(t); } }
+    int numContacts(boolean includeInternal) { try { return (int) NUM_CONTACTS.invokeExact(ctx, includeInternal ? 1 : 0); } catch (Throwable t) { throw new RuntimeException(t); } }
+
+    /** x[3n] R[9n] v[3n] omega[3n] (double), sleeping[n] collection[n] (int): caller-owned off-heap buffers */
+    void downloadBodies(MemorySegment x, MemorySegment R, MemorySegment v, MemorySegment w, MemorySegment sleeping, MemorySegment collection) {
+        try { check((int) DOWNLOAD_BODIES.invokeExact(ctx, x, R, v, w, sleeping, collection)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }
+    }
+    /** out: capacity x am3d_contact; returns the number written */
+    int downloadContacts(MemorySegment out, int capacity, boolean includeInternal) {
+        MemorySegment n = arena.allocate(JAVA_INT);
+        try { check((int) DOWNLOAD_CONTACTS.invokeExact(ctx, out, capacity, includeInternal ? 1 : 0, n)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }
+        return n.get(JAVA_INT, 0);
+    }
+    void timings(MemorySegment am3dTimings) { try { check((int) GET_TIMINGS.invokeExact(ctx, am3dTimings)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    /** MouseImpulse / scripted pushes: v or w may be MemorySegment.NULL (leave unchanged) */
+    void setBodyVelocity(int body, MemorySegment v3, MemorySegment w3) { try { check((int) SET_BODY_VELOCITY.invokeExact(ctx, body, v3, w3)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void addBodyVelocity(int body, MemorySegment dv3, MemorySegment dw3) { try { check((int) ADD_BODY_VELOCITY.invokeExact(ctx, body, dv3, dw3)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void addVelocities(MemorySegment dv, MemorySegment dw) { try { check((int) ADD_VELOCITIES.invokeExact(ctx, dv, dw)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+
+    @Override public void close() {
+        try { int rc = (int) DESTROY.invokeExact(ctx); } catch (Throwable ignored) { }
+        arena.close();
+    }
+}
