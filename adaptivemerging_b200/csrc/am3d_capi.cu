@@ -295,10 +295,12 @@ int am3d_create(int device, am3d_ctx** out) {
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     if (const char* e = getenv("AM3D_PGS_MINB")) c->pgsMinB = atoi(e);
-    if (c->pgsMinB >= 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<4>, 128, 0));
-    else if (c->pgsMinB == 3) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<3>, 128, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<1>, 128, 0));
-    c->coopBlocks = coop ? sms * perSm : 0;
+    // co-resident CTAs per variant: [register cap 0/1][hub support 0/1]
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<1, false>), 128, 0)); c->coopBlocksV[0][0] = coop ? sms * perSm : 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<1, true>), 128, 0));  c->coopBlocksV[0][1] = coop ? sms * perSm : 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<3, false>), 128, 0)); c->coopBlocksV[1][0] = coop ? sms * perSm : 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<3, true>), 128, 0));  c->coopBlocksV[1][1] = coop ? sms * perSm : 0;
+    c->coopBlocks = c->coopBlocksV[0][1];
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
     delete c;

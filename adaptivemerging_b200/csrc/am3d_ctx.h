@@ -161,7 +161,7 @@ struct am3d_ctx {
 
   // ---- broadphase ---------------------------------------------------------------------------------
   std::vector<int> hSmall, hLarge, hPlanes;
-  DevBuf<int> smallList, largeList, planeList;
+  DevBuf<int> smallList, largeList, planeList, largeStart, planeStart;  // special lists are grouped by scene
   int nSmall = 0, nLarge = 0, nPlanes = 0;
   double cellSize = 1.0;
   DevBuf<unsigned long long> cellKey, cellKeySorted;
@@ -173,6 +173,7 @@ struct am3d_ctx {
   DevBuf<int> pairType, pairCap, pairSlot, pairCount, pairOut;
   // raw hits (slot layout)
   DevBuf<double> hitPos, hitNrm, hitViol;
+  DevBuf<int> treeList;  // indices of the candidate pairs that involve a sphere tree
   DevBuf<int> hitMeta;  // [4]: info, bv1, bv2, leaf
   long long nSlots = 0;
 
@@ -229,6 +230,7 @@ struct am3d_ctx {
   cudaEvent_t ev[20];
   bool narrowTimed = false;  // events 16..19 were recorded by the last detect()
   bool evCreated = false;
+  int coopBlocksV[2][2] = {{0, 0}, {0, 0}};
   int coopBlocks = 0;     // co-resident CTAs for the cooperative PGS kernel (0: cooperative launch unsupported)
   int pgsMinB = 1;        // __launch_bounds__ min blocks per SM of the PGS kernels (register cap; AM3D_PGS_MINB)
   int usePersistent = 1;  // 0 never, 1 heuristic, 2 always (AM3D_PGS_PERSISTENT)

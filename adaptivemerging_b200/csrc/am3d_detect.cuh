@@ -158,8 +158,9 @@ __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys,
 }
 
 // one thread per non-plane shape: test against the (few) large shapes and the planes
-__global__ void k_pairs_special(int nsh, const int* __restrict__ shType, const int* __restrict__ shLarge, int nLarge,
-                                const int* __restrict__ largeList, int nPlanes, const int* __restrict__ planeList,
+__global__ void k_pairs_special(int nsh, const int* __restrict__ shType, const int* __restrict__ shLarge,
+                                const int* __restrict__ largeStart, const int* __restrict__ largeList,
+                                const int* __restrict__ planeStart, const int* __restrict__ planeList,
                                 const double* __restrict__ shSize, const double* __restrict__ shRadius, PairCtx C) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nsh) return;
@@ -167,14 +168,15 @@ __global__ void k_pairs_special(int nsh, const int* __restrict__ shType, const i
   if (ty == AM3D_SHAPE_PLANE) return;
   d3 c = ld3(C.bc + 3 * t);
   double r = C.br[t];
-  for (int k = 0; k < nLarge; k++) {
+  int sc = C.scene[C.shBody[t]];
+  for (int k = largeStart[sc]; k < largeStart[sc + 1]; k++) {
     int l = largeList[k];
     if (l == t) continue;
     if (shLarge[t] && t < l) continue;  // large-large pairs once
     if (!sphereBoxOverlap(c, r, ld3(C.bc + 3 * l), C.br[l])) continue;
     tryPair(C, t, l);
   }
-  for (int k = 0; k < nPlanes; k++) {
+  for (int k = planeStart[sc]; k < planeStart[sc + 1]; k++) {
     int pl = planeList[k];
     d3 n = ld3(shSize + 3 * pl);
     double d = shRadius[pl];
@@ -194,7 +196,8 @@ __global__ void k_pairs_special(int nsh, const int* __restrict__ shType, const i
 enum { PT_BOXBOX = 0, PT_PLANEBOX = 1, PT_TREEPLANE = 2, PT_BOXTREE = 3, PT_TREETREE = 4 };
 
 __global__ void k_pair_classify(int np, unsigned long long* __restrict__ pairVal, const int* __restrict__ shType,
-                                int* __restrict__ pairType, int* __restrict__ pairCap) {
+                                int* __restrict__ pairType, int* __restrict__ pairCap, int* __restrict__ treeList,
+                                int* __restrict__ treeCount) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= np) return;
   int a = (int)(pairVal[i] >> 32), b = (int)(pairVal[i] & 0xffffffffu);
@@ -219,6 +222,7 @@ __global__ void k_pair_classify(int np, unsigned long long* __restrict__ pairVal
   if (swap) pairVal[i] = ((unsigned long long)(unsigned)b << 32) | (unsigned)a;
   pairType[i] = t;
   pairCap[i] = (t == PT_BOXBOX || t == PT_PLANEBOX) ? 8 : 0;  // tree pairs: filled by the count pass
+  if (t != PT_BOXBOX && t != PT_PLANEBOX) treeList[atomicAdd(treeCount, 1)] = i;  // order is irrelevant: every pair owns its slots
 }
 
 struct HitOut {
@@ -287,16 +291,12 @@ struct TreeCtx {
 };
 
 template <bool EMIT>
-__global__ void k_narrow_tree(int np, const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairType,
-                              const int* __restrict__ pairSlot, TreeCtx C, HitOut H, int* __restrict__ pairCountOrCap,
-                              int* __restrict__ overflowFlag) {
-  __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TREE_STACK];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int i = blockIdx.x * WARPS_PER_BLOCK + warp;
-  if (i >= np) return;
+__device__ __forceinline__ void narrowTreePair(int i, unsigned long long* stack, const unsigned long long* __restrict__ pairVal,
+                                               const int* __restrict__ pairType, const int* __restrict__ pairSlot,
+                                               const TreeCtx& C, const HitOut& H, int* __restrict__ pairCountOrCap,
+                                               int* __restrict__ overflowFlag) {
+  int lane = threadIdx.x & 31;
   int pt = pairType[i];
-  if (pt != PT_TREEPLANE && pt != PT_BOXTREE && pt != PT_TREETREE) return;
-  unsigned long long* stack = stackMem[warp];
   int a = (int)(pairVal[i] >> 32), b = (int)(pairVal[i] & 0xffffffffu);
   long long base = EMIT ? pairSlot[i] : 0;
   int count = 0;  // warp-uniform
@@ -452,6 +452,23 @@ __global__ void k_narrow_tree(int np, const unsigned long long* __restrict__ pai
     }
   }
   if (lane == 0) pairCountOrCap[i] = count;
+}
+
+// One warp per entry of the tree-pair list written by k_pair_classify (scenes of boxes with a few meshes have a
+// million pairs and a handful of tree pairs); the grid is fixed and the warps stride over the list, whose length
+// lives on the device.
+template <bool EMIT>
+__global__ void k_narrow_tree(const int* __restrict__ treeList, const int* __restrict__ treeCount,
+                              const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairType,
+                              const int* __restrict__ pairSlot, TreeCtx C, HitOut H, int* __restrict__ pairCountOrCap,
+                              int* __restrict__ overflowFlag) {
+  __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TREE_STACK];
+  int warp = threadIdx.x >> 5;
+  int n = *treeCount;
+  for (int t = blockIdx.x * WARPS_PER_BLOCK + warp; t < n; t += gridDim.x * WARPS_PER_BLOCK) {
+    narrowTreePair<EMIT>(treeList[t], stackMem[warp], pairVal, pairType, pairSlot, C, H, pairCountOrCap, overflowFlag);
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

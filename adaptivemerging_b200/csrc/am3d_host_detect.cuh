@@ -29,7 +29,7 @@ static void detect(am3d_ctx* c) {
     if (c->nSmall > 0)
       LAUNCH(c, k_pairs_grid, nblk(c->nSmall), BLK, c->nSmall, c->cellKeySorted.p, c->cellValSorted.p, inv, PC);
     if (c->nLarge > 0 || c->nPlanes > 0)
-      LAUNCH(c, k_pairs_special, nblk(nsh), BLK, nsh, c->shType.p, c->shLarge.p, c->nLarge, c->largeList.p, c->nPlanes,
+      LAUNCH(c, k_pairs_special, nblk(nsh), BLK, nsh, c->shType.p, c->shLarge.p, c->largeStart.p, c->largeList.p, c->planeStart.p,
              c->planeList.p, c->shSize.p, c->shRadius.p, PC);
     np = readInt(c, c->counters.p);
     if ((size_t)np <= c->pairKey.cap) break;
@@ -45,14 +45,18 @@ static void detect(am3d_ctx* c) {
       return cub::DeviceRadixSort::SortPairs(t, b, c->pairKey.p, c->pairKeySorted.p, c->pairVal.p, c->pairValSorted.p, np, 0, endBit, c->stream);
     });
     c->pairType.ensure(np + 1); c->pairCap.ensure(np + 1); c->pairSlot.ensure(np + 1); c->pairCount.ensure(np + 1); c->pairOut.ensure(np + 1);
-    LAUNCH(c, k_pair_classify, nblk(np), BLK, np, c->pairValSorted.p, c->shType.p, c->pairType.p, c->pairCap.p);
+    c->treeList.ensure(np + 1);
+    CK(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(int), c->stream));
+    LAUNCH(c, k_pair_classify, nblk(np), BLK, np, c->pairValSorted.p, c->shType.p, c->pairType.p, c->pairCap.p, c->treeList.p,
+           c->counters.p + 7);
+    int treeGrid = std::min(nblk(np, WARPS_PER_BLOCK), 148 * 16);
     TreeCtx TC{c->shType.p, c->shRoot.p, c->shSize.p, c->shRadius.p, c->shP.p, c->shX.p, c->shR.p, c->ndC.p, c->ndR.p, c->ndFirst.p, c->ndCount.p};
     HitOut HO{c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p};
     bool haveTrees = c->NN > 0;
     CK(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(int), c->stream));
     CK(cudaEventRecord(c->ev[16], c->stream));
     if (haveTrees)
-      LAUNCH(c, k_narrow_tree<false>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
+      LAUNCH(c, k_narrow_tree<false>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
              c->pairSlot.p, TC, HO, c->pairCap.p, c->counters.p + 1);
     CK(cudaEventRecord(c->ev[17], c->stream));
     int nslots = scanTotal(c, c->pairCap, c->pairSlot, np);
@@ -65,7 +69,7 @@ static void detect(am3d_ctx* c) {
     LAUNCH(c, k_narrow_box, nblk(np, 128), 128, np, c->pairValSorted.p, c->pairType.p, c->pairSlot.p, c->shSize.p, c->shRadius.p,
            c->shX.p, c->shR.p, HO, c->pairCount.p);
     if (haveTrees)
-      LAUNCH(c, k_narrow_tree<true>, nblk(np, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, np, c->pairValSorted.p, c->pairType.p,
+      LAUNCH(c, k_narrow_tree<true>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
              c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1);
     CK(cudaEventRecord(c->ev[19], c->stream));
     c->narrowTimed = true;
@@ -96,10 +100,11 @@ static void buildBodyPairs(am3d_ctx* c) {
     c->bp.ensure(nbp + 1);
     LAUNCH(c, k_bpc_fill, nblk(nc), BLK, nc, c->cur.key0.p, c->tmpI0.p, c->tmpI1.p, c->cur.b1.p, c->cur.b2.p, c->flags.p,
            c->cur.bpc.p, c->bp.key.p, c->bp.start.p, c->bp.b1.p, c->bp.b2.p);
+    CK(cudaMemsetAsync(c->counters.p + 8 + (c->totalSteps & 1), 0, sizeof(int), c->stream));
     LAUNCH(c, k_bpc_match, nblk(nbp), BLK, nbp, nc, c->bp.key.p, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p,
            c->bp.nActive.p, c->bp.metricHist.p, c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, c->bp.alive.p,
            c->bpPrev.n, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p, c->bpPrev.metricHist.p, c->bpPrev.stateHist.p,
-           c->bpPrev.nMetric.p, c->bpPrev.nState.p);
+           c->bpPrev.nMetric.p, c->bpPrev.nState.p, c->counters.p + 8 + (c->totalSteps & 1));
   }
   c->bp.n = nbp;
 }
@@ -116,7 +121,8 @@ static void warmStart(am3d_ctx* c) {
     });
   }
   int ns = c->prev.nSorted;
-  int useIdx = c->NN > 0 && ns > 0;
+  // a pair of sphere trees can hold 10^4+ contacts: index last step's contacts when it had such pairs
+  int useIdx = c->NN > 0 && ns > 0 && readInt(c, c->counters.p + 8 + ((c->totalSteps + 1) & 1)) > 64;
   if (useIdx) {  // stable sort of the canonical entries by key1, then by key0
     c->wsKa.ensure(ns + 1); c->wsKb.ensure(ns + 1); c->wsK0s.ensure(ns + 1); c->wsK1s.ensure(ns + 1);
     c->wsIa.ensure(ns + 1); c->wsIb.ensure(ns + 1); c->wsIdx.ensure(ns + 1);

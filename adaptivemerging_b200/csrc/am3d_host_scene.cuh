@@ -122,12 +122,24 @@ static void resetState(am3d_ctx* c) {
     else if (br[s] > thr) { c->hLarge.push_back(s); isLarge[s] = 1; }
     else { c->hSmall.push_back(s); maxSmall = std::max(maxSmall, br[s]); }
   }
-  if (c->hLarge.size() > 4096) {  // degenerate size distribution: fall back to one class
+  if (c->hLarge.size() > 4096 * (size_t)H.nscenes) {  // degenerate size distribution: fall back to one class
     for (int s : c->hLarge) { c->hSmall.push_back(s); isLarge[s] = 0; maxSmall = std::max(maxSmall, br[s]); }
     c->hLarge.clear();
     std::sort(c->hSmall.begin(), c->hSmall.end());
   }
   c->cellSize = maxSmall > 0 ? 2.0 * maxSmall * 1.0000001 : 1.0;
+  // large shapes and planes grouped by scene: a shape only meets the special shapes of its own scene
+  auto sceneOf = [&](int s) { return H.body_scene[H.shape_body[s]]; };
+  auto byScene = [&](std::vector<int>& list, std::vector<int>& start) {
+    std::stable_sort(list.begin(), list.end(), [&](int a, int b) { return sceneOf(a) < sceneOf(b); });
+    start.assign(H.nscenes + 1, 0);
+    for (int s : list) start[sceneOf(s) + 1]++;
+    for (int k = 0; k < H.nscenes; k++) start[k + 1] += start[k];
+  };
+  std::vector<int> largeStart, planeStart;
+  byScene(c->hLarge, largeStart);
+  byScene(c->hPlanes, planeStart);
+  h2dv(c, c->largeStart, largeStart); h2dv(c, c->planeStart, planeStart);
   c->nSmall = (int)c->hSmall.size(); c->nLarge = (int)c->hLarge.size(); c->nPlanes = (int)c->hPlanes.size();
   h2dv(c, c->smallList, c->hSmall); h2dv(c, c->largeList, c->hLarge); h2dv(c, c->planeList, c->hPlanes);
   h2dv(c, c->shLarge, isLarge);

@@ -157,11 +157,13 @@ __global__ void k_bpc_match(int nb, int nc, const unsigned long long* __restrict
                             double* __restrict__ mh, int* __restrict__ sh, int* __restrict__ nm, int* __restrict__ nst,
                             int* __restrict__ alive, int np, const unsigned long long* __restrict__ pkey,
                             const int* __restrict__ pb1, const int* __restrict__ pb2, const double* __restrict__ pmh,
-                            const int* __restrict__ psh, const int* __restrict__ pnm, const int* __restrict__ pnst) {
+                            const int* __restrict__ psh, const int* __restrict__ pnm, const int* __restrict__ pnst,
+                            int* __restrict__ maxCount) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   int end = (b + 1 < nb) ? start[b + 1] : nc;
   count[b] = end - start[b];
+  if (end - start[b] > 64) atomicMax(maxCount, end - start[b]);  // sphere-tree pairs: next step's warm start indexes them
   nActive[b] = 0;
   alive[b] = 1;
   unsigned long long k = key[b];
@@ -308,10 +310,11 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
   int t1 = W.btype[bb1[b]], t2 = W.btype[bb2[b]];
   bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
   if (!boxy) return;  // k_warm_start_plain
+  unsigned long long lastK0 = ~0ULL;
+  int rlo = 0, rhi = 0;
   for (int i = s; i < e; i++) {
     unsigned long long k0 = W.key0[i], k1 = W.key1[i];
-    int rlo, rhi;
-    warmRange(W, k0, rlo, rhi);
+    if (k0 != lastK0) { warmRange(W, k0, rlo, rhi); lastK0 = k0; }  // same (bodies, parts) as the previous contact: same range
     bool vanillaOnly = !boxy;
     bool doBox = boxy;
     if (boxy) {
@@ -752,7 +755,7 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
 // A hub side works on a private copy of the hub's deltaV as of the start of the colour (plus this group's own
 // updates) and hands what it added to hubDelta; k_hub_reduce folds the deltas in after the colour, in a fixed order.
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int MODE>
+template <int MODE, bool HUB>
 __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
                                          double& localMax) {
   int a = S.sgB1[p], b = S.sgB2[p];
@@ -766,7 +769,7 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   double mu = S.sgMu[p];
   int fl = S.sgFlags[p];
   bool clamp = fl & SG_CLAMP;
-  bool hubA = fl & SG_HUB1, hubB = fl & SG_HUB2;
+  const bool hubA = HUB && (fl & SG_HUB1), hubB = HUB && (fl & SG_HUB2);  // HUB = false: the solve has no hub body
   double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
   for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
@@ -887,14 +890,14 @@ __global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __re
   if (r < rEnd) hubReduceRun(r, H, hubDelta, dv);
 }
 
-template <int MODE, int MINB>
+template <int MODE, int MINB, bool HUB>
 __global__ void __launch_bounds__(128, MINB)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
             unsigned long long* __restrict__ iterState) {
   if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
   int p = gBegin + blockIdx.x * blockDim.x + threadIdx.x;
   double localMax = 0;
-  if (p < gEnd) pgsGroup<MODE>(p, S, dv, P, lastIter, localMax);
+  if (p < gEnd) pgsGroup<MODE, HUB>(p, S, dv, P, lastIter, localMax);
   if (MODE == 1) {
     // max |delta lambda| of the sweep (PGS.java:125,159,176): non-negative doubles order like their bit patterns
     for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
@@ -904,8 +907,10 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
 
 // The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
 // colour (two when the colour has hub runs).  Used when the colours are many and small (batched scenes): thousands
-// of tiny launches become grid syncs.  Same Gauss-Seidel sequence as the per-colour launches.
-template <int MINB>
+// of tiny launches become grid barriers.  Same Gauss-Seidel sequence as the per-colour launches.
+// (Measured without gain on B200, so not kept: an own split arrive/wait barrier without the L1 invalidate, L2 prefetch
+// of the next colour's records while waiting, zigzag and ticket-counter distribution of the groups: DESIGN.md.)
+template <int MINB, bool HUB>
 __global__ void __launch_bounds__(128, MINB)
 k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H,
                  SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance,
@@ -916,9 +921,9 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __r
   double dummy = 0;
   for (int c = 0; c < nColors; c++) {
     int g1 = colorStart[c + 1];
-    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0>(p, S, dv, P, 0, dummy);
+    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0, HUB>(p, S, dv, P, 0, dummy);
     grid.sync();
-    if (colorRunStart) {
+    if (HUB) {
       int r1 = colorRunStart[c + 1];
       if (r1 > colorRunStart[c]) {
         for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);
@@ -931,9 +936,9 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __r
     double localMax = 0;
     for (int c = 0; c < nColors; c++) {
       int g1 = colorStart[c + 1];
-      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1>(p, S, dv, P, last, localMax);
+      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1, HUB>(p, S, dv, P, last, localMax);
       grid.sync();
-      if (colorRunStart) {
+      if (HUB) {
         int r1 = colorRunStart[c + 1];
         if (r1 > colorRunStart[c]) {
           for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);

@@ -56,7 +56,7 @@ def build_workload(name, size, merging, y0=None):
         blob = box_stack(n, n, n, pile=(name == "pile"))
         return blob, p, f"{name} {n}x{n}x{n} unit boxes on a plane (config M of BASELINE.json), merging {'on' if merging else 'off'}"
     if name == "funnel":
-        n = size or 100
+        n = size or 20  # BASELINE's config F is n = 100 (100k bodies); see DESIGN.md for why the default is smaller
         tmpl = load_blob(os.path.join(GOLDEN, "scene_funnel_template.npz"))
         p = apply_overrides(p, tmpl.overrides)
         y0 = 0.6 if y0 is None else y0
@@ -195,13 +195,13 @@ def main():
     ap.add_argument("--size", type=int, default=0)
     ap.add_argument("--settle", type=int, default=-1,
                     help="untimed steps before the warm-up so that the workload is in its loaded phase "
-                         "(default: 150 batch = towers collapsing onto the platform, 20 stack/pile, 260 funnel = bodies "
-                         "piled up)")
+                         "(default: 150 batch = towers collapsing onto the platform, 20 stack/pile, 35 funnel = second layer "
+                         "landing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.settle < 0:
-        args.settle = {"batch": 150, "stack": 20, "pile": 20, "funnel": 60}[args.workload]
+        args.settle = {"batch": 150, "stack": 20, "pile": 20, "funnel": 35}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
