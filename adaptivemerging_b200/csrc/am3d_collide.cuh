@@ -104,9 +104,10 @@ __device__ __forceinline__ bool satEdge(double expr1, double expr2, double n1, d
   return true;
 }
 
-// Returns the number of hits (0..8) written to out[].
+// Returns the number of hits (0..8) handed to out.set(k, point, normal, info, violation), k = 0..n-1 in order.
+template <class OUT>
 __device__ inline int collideBoxBox(const d3& p1, const m3& R1, const d3& side1, double radius1, const d3& p2,
-                                    const m3& R2, const d3& side2, double radius2, Hit* out) {
+                                    const m3& R2, const d3& side2, double radius2, OUT& out) {
   d3 p = vsub(p2, p1);
   if (vlen(p) > radius1 + radius2) return 0;
   d3 pp = mtransformT(R1, p);
@@ -179,10 +180,7 @@ __device__ inline int collideBoxBox(const d3& p1, const m3& R1, const d3& side1,
     pb = vscaleAdd(beta, ub, pb);
     d3 pos = vadd(pa, pb);
     pos = vscale(0.5, pos);
-    out[0].pos = pos;
-    out[0].normal = normal;
-    out[0].info = 0;
-    out[0].violation = -depth;
+    out.set(0, pos, normal, 0, -depth);
     return 1;
   }
 
@@ -236,10 +234,7 @@ __device__ inline int collideBoxBox(const d3& p1, const m3& R1, const d3& side1,
     for (int i = 0; i < 3; i++) pt.setc(i, center.get(i) + k1 * Rb.el(i, a1) + k2 * Rb.el(i, a2));
     double dep = Sa.get(codeN) - (normal2.x * pt.x + normal2.y * pt.y + normal2.z * pt.z);
     if (dep >= 0) {
-      out[cnum].pos = d3(pt.x + pa.x, pt.y + pa.y, pt.z + pa.z);
-      out[cnum].normal = normal;
-      out[cnum].info = cnum;
-      out[cnum].violation = -dep;
+      out.set(cnum, d3(pt.x + pa.x, pt.y + pa.y, pt.z + pa.z), normal, cnum, -dep);
       cnum++;
     }
   }
@@ -247,7 +242,8 @@ __device__ inline int collideBoxBox(const d3& p1, const m3& R1, const d3& side1,
 }
 
 // box (T,size,radius) vs plane (n,d): hits per penetrating corner, info = corner id
-__device__ inline int collideBoxPlane(const xf& T, const d3& size, double radius, const d3& n, double d, Hit* out) {
+template <class OUT>
+__device__ inline int collideBoxPlane(const xf& T, const d3& size, double radius, const d3& n, double d, OUT& out) {
   if (T.t.x * n.x + T.t.y * n.y + T.t.z * n.z + d > radius) return 0;
   d3 p = vscale(0.5, size);
   int cnt = 0;
@@ -257,10 +253,7 @@ __device__ inline int collideBoxPlane(const xf& T, const d3& size, double radius
     q = xfP(T, q);
     double s = q.x * n.x + q.y * n.y + q.z * n.z + d;
     if (s < 0) {
-      out[cnt].pos = q;
-      out[cnt].normal = n;
-      out[cnt].info = k;
-      out[cnt].violation = s;
+      out.set(cnt, q, n, k, s);
       cnt++;
     }
   }

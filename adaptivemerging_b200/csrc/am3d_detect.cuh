@@ -240,6 +240,14 @@ __device__ __forceinline__ void writeHit(const HitOut& H, long long slot, const 
   reinterpret_cast<int4*>(H.meta)[slot] = m;
 }
 
+struct HitSlotSink {
+  const HitOut& H;
+  long long base;
+  __device__ __forceinline__ void set(int k, const d3& p, const d3& n, int info, double viol) const {
+    writeHit(H, base + k, p, n, viol, info, AM3D_BV_NULL, AM3D_BV_NULL, -1);
+  }
+};
+
 // box x box and plane x box: one thread per pair
 __global__ void k_narrow_box(int np, const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairType,
                              const int* __restrict__ pairSlot, const double* __restrict__ shSize, const double* __restrict__ shRadius,
@@ -250,21 +258,18 @@ __global__ void k_narrow_box(int np, const unsigned long long* __restrict__ pair
   int pt = pairType[i];
   if (pt != PT_BOXBOX && pt != PT_PLANEBOX) return;
   int a = (int)(pairVal[i] >> 32), b = (int)(pairVal[i] & 0xffffffffu);
-  Hit hits[8];
+  HitSlotSink sink{H, pairSlot[i]};  // hits go straight to the pair's slots: no per-thread staging array in local memory
   int n;
   if (pt == PT_BOXBOX) {
     n = collideBoxBox(ld3(shX + 3 * a), ldm(shR + 9 * a), ld3(shSize + 3 * a), shRadius[a], ld3(shX + 3 * b),
-                      ldm(shR + 9 * b), ld3(shSize + 3 * b), shRadius[b], hits);
+                      ldm(shR + 9 * b), ld3(shSize + 3 * b), shRadius[b], sink);
   } else {
     int pl = a, bx = b;
     xf T;
     T.R = ldm(shR + 9 * bx);
     T.t = ld3(shX + 3 * bx);
-    n = collideBoxPlane(T, ld3(shSize + 3 * bx), shRadius[bx], ld3(shSize + 3 * pl), shRadius[pl], hits);
+    n = collideBoxPlane(T, ld3(shSize + 3 * bx), shRadius[bx], ld3(shSize + 3 * pl), shRadius[pl], sink);
   }
-  long long base = pairSlot[i];
-  for (int k = 0; k < n; k++)
-    writeHit(H, base + k, hits[k].pos, hits[k].normal, hits[k].violation, hits[k].info, AM3D_BV_NULL, AM3D_BV_NULL, -1);
   pairCount[i] = n;
 }
 
