@@ -777,13 +777,28 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
 #pragma unroll
   for (int k = 0; k < 6; k++) { acc1[k] = 0.0; acc2[k] = 0.0; }
+  // The chain over the contacts of a pair is sequential; the record of contact c+1 is loaded into a second register
+  // set BEFORE the dependent arithmetic of contact c so that its latency hides behind it (the hub variant has no
+  // registers to spare and only prefetches it into L2).
+  constexpr bool PIPE = !HUB;
+  double Q[24], N[24];
+  if (PIPE && cnt > 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) ld4(PK0 + 4 * k, Q + 4 * k);
+  }
   for (int c = 0; c < cnt; c++) {
     double* PK = S.scP + 24 * (size_t)(start + c);
-    if (c + 1 < cnt) { prefetchL2(PK + 24); prefetchL2(PK + 40); }  // next contact: hide the load latency of the sequential chain
-    double Q[24];
+    if (PIPE) {
+      if (c + 1 < cnt) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) ld4(PK + 4 * k, Q + 4 * k);
-    ld4cg(PK + 20, Q + 20);  // D[2] and lambda: rewritten every sweep
+        for (int k = 0; k < 6; k++) ld4(PK + 24 + 4 * k, N + 4 * k);
+        if (c + 2 < cnt) { prefetchL2(PK + 48); prefetchL2(PK + 64); }
+      }
+    } else {
+      if (c + 1 < cnt) { prefetchL2(PK + 24); prefetchL2(PK + 40); }
+#pragma unroll
+      for (int k = 0; k < 6; k++) ld4(PK + 4 * k, Q + 4 * k);
+    }
     d3 dir[3] = {{Q[0], Q[1], Q[2]}, {Q[3], Q[4], Q[5]}, {Q[6], Q[7], Q[8]}};
     d3 r1 = {Q[9], Q[10], Q[11]}, r2 = {Q[12], Q[13], Q[14]};
     double lam[3] = {Q[21], Q[22], Q[23]};
@@ -835,6 +850,10 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
         else st = AM3D_CS_CLEAR;
         S.scState[start + c] = st;
       }
+    }
+    if (PIPE) {
+#pragma unroll
+      for (int k = 0; k < 24; k++) Q[k] = N[k];
     }
   }
   if (a >= 0) {
