@@ -139,13 +139,13 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(kernel):
+def measured_traffic(kernel, workload):
     """DRAM bytes (read + write) per contact per PGS iteration of the sweep kernel, from the committed
-    `ncu --set full` capture (profiles/r1_traffic.json; dram__bytes_read.sum + dram__bytes_write.sum divided by
-    the contact-iterations of the captured launches)."""
+    `ncu --set full` capture of the same workload (profiles/r1_traffic.json; dram__bytes_read.sum +
+    dram__bytes_write.sum divided by the contact-iterations of the captured launch)."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            d = json.load(f)[kernel]
+            d = json.load(f)[kernel][{"pile": "stack"}.get(workload, workload)]
         return float(d["dram_bytes_per_contact_iter"]), d["source"]
     except Exception:
         return None, None
@@ -312,7 +312,7 @@ def main():
     solve_launches = max(float(counts[4]), 1.0)
     persistent = solve_launches <= 2 * args.steps  # one cooperative launch per solve vs one launch per colour per iteration
     kernel = "k_pgs_persistent" if persistent else "k_pgs_color<1>"
-    traffic_ratio, traffic_src = measured_traffic(kernel)
+    traffic_ratio, traffic_src = measured_traffic(kernel, args.workload)
     contact_iters_per_launch = (row_updates / 3.0) / solve_launches
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -2,7 +2,7 @@ mkdir -p gpurun_out/r1
 timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 400 python bench.py > gpurun_out/r1/bench_batch.json 2> gpurun_out/r1/bench_batch.err; tail -c 400 gpurun_out/r1/bench_batch.json
-timeout 300 python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/r1/bench_reference_batch.json 2>&1
+timeout 300 python bench.py --impl reference --steps 40 --warmup 3 > gpurun_out/r1/bench_reference_batch.json 2>&1
 timeout 300 python bench.py --workload stack --merging 0 > gpurun_out/r1/bench_stack_m0.json 2> gpurun_out/r1/err1
 timeout 300 python bench.py --workload stack --merging 1 --no-cpu-baseline > gpurun_out/r1/bench_stack_m1.json 2> gpurun_out/r1/err2
 timeout 300 python bench.py --workload pile --merging 1 --no-cpu-baseline > gpurun_out/r1/bench_pile_m1.json 2> gpurun_out/r1/err3
