@@ -1,0 +1,61 @@
+"""The C ABI's contract (include/am3d.h): error codes instead of exceptions, call-order checks, unsupported reference
+options refused loudly, and reset() = RigidBodySystem.reset (:390-410): the run after a reset repeats the first
+run bit for bit."""
+import numpy as np
+import pytest
+
+from adaptivemerging_b200 import _capi
+from adaptivemerging_b200.ctypes_defs import apply_overrides, default_params
+from adaptivemerging_b200.system import RigidBodySystem
+from tests.util import golden_scene, params, small_pile
+
+pytestmark = pytest.mark.gpu
+
+
+def _code(exc):
+    return exc.value.code
+
+
+def test_call_order_and_bad_arguments():
+    s = RigidBodySystem(0)
+    with pytest.raises(_capi.Am3dError) as e:
+        s.advanceTime(0.05)
+    assert _code(e) == _capi.ESTATE           # step before upload_scene
+    s.load(small_pile(), params())
+    with pytest.raises(_capi.Am3dError) as e:
+        s.set_body_velocity(10 ** 6, v=np.zeros(3))
+    assert _code(e) == _capi.EINVAL
+    s.advanceTime(0.05, 3)
+    assert s.timings().n_contacts > 0
+    s.close()
+
+
+@pytest.mark.parametrize("field", ["shuffle", "enable_post_stabilization", "use_coriolis", "merge_cycle_condition",
+                                   "metric_position_level", "collection_cd"])
+def test_unsupported_reference_options_are_refused(field):
+    s = RigidBodySystem(0)
+    p = default_params()
+    setattr(p, field, 1)
+    with pytest.raises(_capi.Am3dError) as e:
+        s.set_params(p)
+    assert _code(e) == _capi.EUNSUPPORTED
+    s.close()
+
+
+def test_reset_repeats_the_run_bit_for_bit():
+    blob = small_pile(4, 5, 4)   # merges into one pinned collection with the plane within ~40 steps
+    p = params()
+    s = RigidBodySystem(0).load(blob, p)
+    s.advanceTime(0.05, 120)
+    first, ev1 = s.bodies(), s.events().tolist()
+    s.reset()
+    assert s.totalSteps == 0
+    b0 = s.bodies()
+    assert np.array_equal(b0["x"], blob.a["body_x"].reshape(-1, 3)) and (b0["collection"] < 0).all()
+    s.advanceTime(0.05, 120)
+    second, ev2 = s.bodies(), s.events().tolist()
+    for k in ("x", "R", "v", "omega"):
+        assert np.array_equal(first[k].view(np.uint64), second[k].view(np.uint64)), k
+    assert np.array_equal(first["collection"], second["collection"])
+    assert ev1 == ev2 and len(ev1) > 0
+    s.close()
