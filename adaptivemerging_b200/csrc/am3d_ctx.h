@@ -163,6 +163,7 @@ struct am3d_ctx {
   std::vector<int> hSmall, hLarge, hPlanes;
   DevBuf<int> smallList, largeList, planeList, largeStart, planeStart;  // special lists are grouped by scene
   int nSmall = 0, nLarge = 0, nPlanes = 0;
+  bool haveComposites = false;  // some body owns more than one shape: pair keys carry the part indices
   double cellSize = 1.0;
   DevBuf<unsigned long long> cellKey, cellKeySorted;
   DevBuf<int> cellVal, cellValSorted;

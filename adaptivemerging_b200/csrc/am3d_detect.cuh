@@ -97,7 +97,16 @@ struct PairCtx {
   unsigned long long* pairVal;
   int* counter;
   int cap;
+  int bodyBits, partBits;  // the pair SORT key is (bodyLo, bodyHi[, partLo, partHi]) packed without gaps: fewer radix passes
 };
+// canonical contact-order key of a shape pair
+__device__ __forceinline__ unsigned long long pairKey0(const int* __restrict__ shBody, const int* __restrict__ bShapeFirst, int sa, int sb) {
+  int ba = shBody[sa], bb = shBody[sb];
+  int slo = ba < bb ? sa : sb, shi = ba < bb ? sb : sa;
+  int blo = shBody[slo], bhi = shBody[shi];
+  unsigned long long plo = slo - bShapeFirst[blo], phi = shi - bShapeFirst[bhi];
+  return ((unsigned long long)blo << 40) | ((unsigned long long)bhi << 16) | (plo << 8) | phi;
+}
 
 // top-level filter of broadPhase :692-693 + pair orientation (list order of RigidBodySystem.bodies)
 __device__ __forceinline__ void tryPair(const PairCtx& C, int sa, int sb) {
@@ -118,7 +127,9 @@ __device__ __forceinline__ void tryPair(const PairCtx& C, int sa, int sb) {
   int slo = ba < bb ? sa : sb, shi = ba < bb ? sb : sa;
   int blo = C.shBody[slo], bhi = C.shBody[shi];
   unsigned long long plo = slo - C.bShapeFirst[blo], phi = shi - C.bShapeFirst[bhi];
-  C.pairKey[idx] = ((unsigned long long)blo << 40) | ((unsigned long long)bhi << 16) | (plo << 8) | phi;
+  unsigned long long k = ((unsigned long long)blo << C.bodyBits) | (unsigned long long)bhi;
+  if (C.partBits) k = (k << 16) | (plo << 8) | phi;
+  C.pairKey[idx] = k;
   C.pairVal[idx] = ((unsigned long long)(unsigned)first << 32) | (unsigned)second;
 }
 
@@ -127,7 +138,8 @@ __device__ __forceinline__ bool sphereBoxOverlap(const d3& ca, double ra, const 
   return fabs(ca.x - cb.x) <= r && fabs(ca.y - cb.y) <= r && fabs(ca.z - cb.z) <= r;
 }
 
-// one thread per small shape: sweep the 27 neighbouring cells in the sorted cell-code array
+// one thread per small shape: its own cell (partners with a larger shape id) and the 13 neighbouring cells of the
+// "positive" half space (all partners), located in the sorted cell-code array: every pair is met exactly once
 __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
                              double inv, PairCtx C) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +152,8 @@ __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys,
   for (int dz = -1; dz <= 1; dz++)
     for (int dy = -1; dy <= 1; dy++)
       for (int dx = -1; dx <= 1; dx++) {
+        const bool own = dx == 0 && dy == 0 && dz == 0;
+        if (!own && (dz < 0 || (dz == 0 && (dy < 0 || (dy == 0 && dx < 0))))) continue;
         int jx = ix + dx, jy = iy + dy, jz = iz + dz;
         if (jx < 0 || jy < 0 || jz < 0 || jx > 16383 || jy > 16383 || jz > 16383) continue;
         unsigned long long k = cellCode(jx, jy, jz, sc);
@@ -150,7 +164,7 @@ __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys,
         }
         for (int j = lo; j < n && keys[j] == k; j++) {
           int t = vals[j];
-          if (t <= s) continue;
+          if (own && t <= s) continue;
           if (!sphereBoxOverlap(c, r, ld3(C.bc + 3 * t), C.br[t])) continue;
           tryPair(C, s, t);
         }
@@ -485,7 +499,7 @@ struct ContactOut {
   double *pW, *nW, *t1W, *t2W, *pB1, *nB1, *t1B1, *t2B1, *viol, *prevViol, *lam, *lamWarm;
 };
 
-__global__ void k_contact_set(int np, const unsigned long long* __restrict__ pairKey,
+__global__ void k_contact_set(int np, const int* __restrict__ bShapeFirst,
                               const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairSlot,
                               const int* __restrict__ pairCount, const int* __restrict__ pairOut,
                               const int* __restrict__ shBody, const double* __restrict__ x, const double* __restrict__ R,
@@ -500,7 +514,7 @@ __global__ void k_contact_set(int np, const unsigned long long* __restrict__ pai
   xf T1;
   T1.R = ldm(R + 9 * b1);
   T1.t = ld3(x + 3 * b1);
-  unsigned long long k0 = pairKey[i];
+  unsigned long long k0 = pairKey0(shBody, bShapeFirst, s1, s2);
   long long slot = pairSlot[i];
   int out = pairOut[i];
   for (int k = 0; k < n; k++, slot++, out++) {

@@ -25,7 +25,8 @@ static void detect(am3d_ctx* c) {
   for (int attempt = 0; attempt < 3; attempt++) {
     CK(cudaMemsetAsync(c->counters.p, 0, sizeof(int), c->stream));
     PairCtx PC{c->shBody.p, c->bShapeFirst.p, c->parent.p, c->flags.p, c->scene.p, c->stamp.p, c->shBoundC.p, c->shBoundR.p,
-               c->pairKey.p, c->pairVal.p, c->counters.p, (int)std::min<size_t>(c->pairKey.cap, 0x7fffffff)};
+               c->pairKey.p, c->pairVal.p, c->counters.p, (int)std::min<size_t>(c->pairKey.cap, 0x7fffffff),
+               bitsFor((unsigned long long)c->NB), c->haveComposites ? 16 : 0};
     if (c->nSmall > 0)
       LAUNCH(c, k_pairs_grid, nblk(c->nSmall), BLK, c->nSmall, c->cellKeySorted.p, c->cellValSorted.p, inv, PC);
     if (c->nLarge > 0 || c->nPlanes > 0)
@@ -40,7 +41,7 @@ static void detect(am3d_ctx* c) {
   c->T.n_pairs = np;
   int nc = 0;
   if (np > 0) {
-    int endBit = std::min(64, 40 + bitsFor((unsigned long long)c->NB));
+    int endBit = 2 * bitsFor((unsigned long long)c->NB) + (c->haveComposites ? 16 : 0);
     cubRun(c, [&](void* t, size_t& b) {
       return cub::DeviceRadixSort::SortPairs(t, b, c->pairKey.p, c->pairKeySorted.p, c->pairVal.p, c->pairValSorted.p, np, 0, endBit, c->stream);
     });
@@ -80,7 +81,7 @@ static void detect(am3d_ctx* c) {
                   c->cur.state.p, c->cur.isNew.p, c->cur.key0.p, c->cur.key1.p, c->cur.pW.p, c->cur.nW.p, c->cur.t1W.p,
                   c->cur.t2W.p, c->cur.pB1.p, c->cur.nB1.p, c->cur.t1B1.p, c->cur.t2B1.p, c->cur.viol.p, c->cur.prevViol.p,
                   c->cur.lam.p, c->cur.lamWarm.p};
-    LAUNCH(c, k_contact_set, nblk(np, 128), 128, np, c->pairKeySorted.p, c->pairValSorted.p, c->pairSlot.p, c->pairCount.p,
+    LAUNCH(c, k_contact_set, nblk(np, 128), 128, np, c->bShapeFirst.p, c->pairValSorted.p, c->pairSlot.p, c->pairCount.p,
            c->pairOut.p, c->shBody.p, c->x.p, c->R.p, c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p, CO);
   }
   c->cur.n = nc;

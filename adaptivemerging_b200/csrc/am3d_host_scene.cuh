@@ -115,6 +115,8 @@ static void resetState(am3d_ctx* c) {
     std::nth_element(tmp.begin(), tmp.begin() + tmp.size() / 2, tmp.end());
     thr = 3.0 * tmp[tmp.size() / 2];
   }
+  c->haveComposites = false;
+  for (int b = 0; b < H.nb; b++) if (H.body_shape_count[b] > 1) c->haveComposites = true;
   c->hSmall.clear(); c->hLarge.clear(); c->hPlanes.clear();
   std::vector<int> isLarge(H.nsh, 0);
   for (int s = 0; s < H.nsh; s++) {
