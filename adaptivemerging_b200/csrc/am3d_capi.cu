@@ -315,6 +315,11 @@ int am3d_destroy(am3d_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->evCreated) for (int i = 0; i < 20; i++) cudaEventDestroy(c->ev[i]);
+  if (c->copyStream) {
+    cudaStreamSynchronize(c->copyStream);
+    cudaEventDestroy(c->evSnap); cudaEventDestroy(c->evCopied);
+    cudaStreamDestroy(c->copyStream);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return AM3D_OK;
@@ -367,23 +372,61 @@ int am3d_sync(am3d_ctx* c) {
 int am3d_num_bodies(const am3d_ctx* c) { return c ? c->NB : AM3D_EINVAL; }
 int am3d_total_steps(const am3d_ctx* c) { return c ? c->totalSteps : AM3D_EINVAL; }
 
+// Outbound read of the body state (what Display reads after a step).  The state is snapshot into staging buffers on
+// the step's stream and copied to the host on a second stream, so that with the _async form the copy of step N runs
+// under the kernels of step N+1; am3d_wait_download() (or the next download) waits for it.
+__global__ void k_body_flags_out(int nb, const int* __restrict__ parent, const int* __restrict__ flags, int* __restrict__ sleeping,
+                                 int* __restrict__ collection) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  int p = parent[i];
+  int t = p >= 0 ? p : i;
+  sleeping[i] = (flags[t] & AM3D_F_SLEEPING) ? 1 : 0;
+  collection[i] = p >= 0 ? p - nb : -1;
+}
+static void downloadBodies(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
+  if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
+  size_t nb = c->NB;
+  if (!c->copyStream) {
+    CK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->evSnap, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming));
+  }
+  if (c->copyPending) { CK(cudaEventSynchronize(c->evCopied)); c->copyPending = false; }  // staging is free again
+  c->stD.ensure(18 * nb + 8); c->stI.ensure(2 * nb + 8);
+  double *sx = c->stD.p, *sR = sx + 3 * nb, *sv = sR + 9 * nb, *sw = sv + 3 * nb;
+  int *ssl = c->stI.p, *sco = ssl + nb;
+  if (x) CK(cudaMemcpyAsync(sx, c->x.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (R) CK(cudaMemcpyAsync(sR, c->R.p, 9 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (v) CK(cudaMemcpyAsync(sv, c->v.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (omega) CK(cudaMemcpyAsync(sw, c->w.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  if (sleeping || collection) LAUNCH(c, k_body_flags_out, nblk((int)nb), BLK, (int)nb, c->parent.p, c->flags.p, ssl, sco);
+  CK(cudaEventRecord(c->evSnap, c->stream));
+  CK(cudaStreamWaitEvent(c->copyStream, c->evSnap, 0));
+  if (x) CK(cudaMemcpyAsync(x, sx, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+  if (R) CK(cudaMemcpyAsync(R, sR, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+  if (v) CK(cudaMemcpyAsync(v, sv, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+  if (omega) CK(cudaMemcpyAsync(omega, sw, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->copyStream));
+  if (sleeping) CK(cudaMemcpyAsync(sleeping, ssl, nb * sizeof(int), cudaMemcpyDeviceToHost, c->copyStream));
+  if (collection) CK(cudaMemcpyAsync(collection, sco, nb * sizeof(int), cudaMemcpyDeviceToHost, c->copyStream));
+  CK(cudaEventRecord(c->evCopied, c->copyStream));
+  c->copyPending = true;
+}
+int am3d_download_bodies_async(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
+  API_BEGIN(c)
+  downloadBodies(c, x, R, v, omega, sleeping, collection);
+  API_END(c)
+}
+int am3d_wait_download(am3d_ctx* c) {
+  API_BEGIN(c)
+  if (c->copyPending) { CK(cudaEventSynchronize(c->evCopied)); c->copyPending = false; }
+  API_END(c)
+}
 int am3d_download_bodies(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
   API_BEGIN(c)
-  if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
-  int nb = c->NB;
-  if (x) CK(cudaMemcpyAsync(x, c->x.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (R) CK(cudaMemcpyAsync(R, c->R.p, 9 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (v) CK(cudaMemcpyAsync(v, c->v.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  if (omega) CK(cudaMemcpyAsync(omega, c->w.p, 3 * nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  std::vector<int> fl(c->NS), par(nb);
-  CK(cudaMemcpyAsync(fl.data(), c->flags.p, c->NS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(par.data(), c->parent.p, nb * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < nb; i++) {
-    int t = par[i] >= 0 ? par[i] : i;
-    if (sleeping) sleeping[i] = (fl[t] & AM3D_F_SLEEPING) ? 1 : 0;
-    if (collection) collection[i] = par[i] >= 0 ? par[i] - nb : -1;
-  }
+  downloadBodies(c, x, R, v, omega, sleeping, collection);
+  CK(cudaEventSynchronize(c->evCopied));
+  c->copyPending = false;
   API_END(c)
 }
 

@@ -229,6 +229,11 @@ struct am3d_ctx {
   // ---- timing --------------------------------------------------------------------------------------
   am3d_timings T;
   cudaEvent_t ev[20];
+  cudaStream_t copyStream = nullptr;  // device -> host copies of the body state run beside the next step
+  cudaEvent_t evSnap = nullptr, evCopied = nullptr;
+  bool copyPending = false;
+  DevBuf<double> stD;  // snapshot of x R v w for the copy stream
+  DevBuf<int> stI;     // sleeping, collection
   bool narrowTimed = false;  // events 16..19 were recorded by the last detect()
   bool evCreated = false;
   int coopBlocksV[2][2] = {{0, 0}, {0, 0}};

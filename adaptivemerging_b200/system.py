@@ -129,6 +129,16 @@ class RigidBodySystem:
         self._ck(self._L.am3d_download_bodies(self._h, _p(x), _p(R), _p(v), _p(w), _p(sl), _p(co)))
         return dict(x=x, R=R, v=v, omega=w, sleeping=sl, collection=co)
 
+    def bodies_async(self, out):
+        """Start the download of the body state into `out` (pinned arrays as returned by bodies()); it completes under
+        the next advanceTime.  wait_bodies() (or the next download) makes `out` valid."""
+        x, R, v, w, sl, co = out["x"], out["R"], out["v"], out["omega"], out["sleeping"], out["collection"]
+        self._ck(self._L.am3d_download_bodies_async(self._h, _p(x), _p(R), _p(v), _p(w), _p(sl), _p(co)))
+        return out
+
+    def wait_bodies(self):
+        self._ck(self._L.am3d_wait_download(self._h))
+
     def upload_bodies(self, x, R, v, omega):
         x, R, v, omega = [np.ascontiguousarray(a, np.float64) for a in (x, R, v, omega)]
         self._ck(self._L.am3d_upload_bodies(self._h, _p(x), _p(R), _p(v), _p(omega)))

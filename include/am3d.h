@@ -287,6 +287,12 @@ int am3d_upload_bodies(am3d_ctx* ctx, const double* x, const double* R, const do
 int am3d_num_bodies(const am3d_ctx* ctx);
 int am3d_download_bodies(am3d_ctx* ctx, double* x, double* R, double* v, double* omega,
                          int32_t* sleeping, int32_t* collection /* -1 or collection slot */);
+/* Same read, not waited for: the state as of this call is snapshot on the device and copied to the (pinned) host
+ * buffers on a second stream while the next am3d_step runs; the buffers are valid after am3d_wait_download() or the
+ * next download call.  Lets a front end draw step N while step N+1 is computed. */
+int am3d_download_bodies_async(am3d_ctx* ctx, double* x, double* R, double* v, double* omega,
+                               int32_t* sleeping, int32_t* collection);
+int am3d_wait_download(am3d_ctx* ctx);
 int am3d_num_contacts(am3d_ctx* ctx, int include_internal);
 int am3d_download_contacts(am3d_ctx* ctx, am3d_contact* out, int capacity, int include_internal,
                            int* count);
