@@ -15,7 +15,7 @@ EXPORTS = [
     "am3d_set_params", "am3d_get_params", "am3d_reset", "am3d_step", "am3d_step_async", "am3d_sync",
     "am3d_set_body_velocity", "am3d_add_body_velocity", "am3d_upload_bodies", "am3d_num_bodies",
     "am3d_download_bodies", "am3d_num_contacts", "am3d_download_contacts", "am3d_num_bpcs", "am3d_download_bpcs",
-    "am3d_get_timings", "am3d_total_steps", "am3d_detect", "am3d_upload_contacts", "am3d_solve",
+    "am3d_get_timings", "am3d_total_steps", "am3d_detect", "am3d_solve",
     "am3d_download_deltav", "am3d_set_lambdas", "am3d_stats", "am3d_download_solve_order", "am3d_mark", "am3d_elapsed_ms",
     "am3d_num_events", "am3d_download_events", "am3d_record_orders", "am3d_download_order", "am3d_num_internal_bpcs",
     "am3d_download_internal_bpcs", "am3d_download_collection", "am3d_set_option", "am3d_add_velocities",

@@ -706,11 +706,4 @@ int am3d_debug_solve_row(am3d_ctx* c, int contact, double* out /* [50] */) {
   API_END(c)
 }
 
-int am3d_upload_contacts(am3d_ctx* c, const am3d_contact* in, int count) {
-  (void)in; (void)count;
-  if (!c) return AM3D_EINVAL;
-  c->lastError = "am3d_upload_contacts is not built yet";
-  return AM3D_EUNSUPPORTED;
-}
-
 }  // extern "C"

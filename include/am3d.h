@@ -308,9 +308,6 @@ int am3d_total_steps(const am3d_ctx* ctx);
 /* broadphase + narrowphase + Contact.set from the current body state
  * (CollisionProcessor.collisionDetection :91-102) */
 int am3d_detect(am3d_ctx* ctx);
-/* load an external contact list (e.g. the oracle's) as the current external
- * contacts: frame given in world coordinates, lambda = warm-start values */
-int am3d_upload_contacts(am3d_ctx* ctx, const am3d_contact* in, int count);
 /* the full solve (CollisionProcessor.solveLCP :108-137 → PGS.solve) on the
  * current contacts; fills lambda, deltaV and contact states */
 int am3d_solve(am3d_ctx* ctx, double dt);
