@@ -86,3 +86,32 @@ def test_free_running_without_merging(scene):
         assert np.abs(g["x"] - o["x"]).max() < 1e-9, step
         assert np.abs(g["v"] - o["v"]).max() < 1e-9, step
         assert np.array_equal(g["sleeping"], o["sleeping"]), step
+
+
+def test_lcp_residuals_against_unpermuted_reference():
+    """North-star parity mode 3: complementarity residuals of the GPU's colour-ordered solve next to those of the
+    reference's own (list-order) Gauss-Seidel on the same contacts.  w = b + J dv + c*lambda; normal rows:
+    |min(lambda, w)|, friction rows: cone violation and |w_t| strictly inside the cone."""
+    from oracle.oracle import Oracle
+    blob = small_pile(4, 5, 4)
+    gpu, cpu = _pair(blob, enable_merging=0)
+    ref = Oracle(blob, params(enable_merging=0))
+    gpu.record_orders(True)
+    for _ in range(25):
+        cpu.step(0.05)
+        ref.step(0.05)
+    b = cpu.bodies()
+    gpu.upload_bodies(b["x"], b["R"], b["v"], b["omega"])
+    assert gpu.detect() == cpu.detect() == ref.detect() > 0
+    gpu.solve(0.05)
+    cpu.apply_external_forces()
+    assert cpu.solve(0.05, gpu.order(0)) == 0       # the oracle now holds exactly the GPU's lambda and deltaV
+    ref.apply_external_forces()
+    ref.solve(0.05)                                 # the reference's own order
+    r_gpu, r_ref = cpu.residuals(), ref.residuals()
+    print(f"\nLCP residuals after 30 sweeps, {int(r_gpu[3])} contacts: colour order (GPU) normal {r_gpu[0]:.3e} cone "
+          f"{r_gpu[1]:.3e} tangential {r_gpu[2]:.3e} | reference order normal {r_ref[0]:.3e} cone {r_ref[1]:.3e} "
+          f"tangential {r_ref[2]:.3e}")
+    assert r_gpu[3] == r_ref[3] > 0
+    assert r_gpu[1] <= 1e-12 and r_ref[1] <= 1e-12                  # projections hold exactly on both sides
+    assert r_gpu[0] <= max(3 * r_ref[0], 1e-3) and r_gpu[2] <= max(3 * r_ref[2], 1e-3)
