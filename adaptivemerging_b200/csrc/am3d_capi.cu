@@ -294,13 +294,10 @@ int am3d_create(int device, am3d_ctx** out) {
     int coop = 0, sms = 0, perSm = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    if (const char* e = getenv("AM3D_PGS_MINB")) c->pgsMinB = atoi(e);
-    // co-resident CTAs per variant: [register cap 0/1][hub support 0/1]
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<1, false>), 128, 0)); c->coopBlocksV[0][0] = coop ? sms * perSm : 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<1, true>), 128, 0));  c->coopBlocksV[0][1] = coop ? sms * perSm : 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<3, false>), 128, 0)); c->coopBlocksV[1][0] = coop ? sms * perSm : 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (k_pgs_persistent<3, true>), 128, 0));  c->coopBlocksV[1][1] = coop ? sms * perSm : 0;
-    c->coopBlocks = c->coopBlocksV[0][1];
+    // co-resident CTAs of the cooperative kernel, per variant [hub support]
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<false>, 128, 0)); c->coopBlocksV[0] = coop ? sms * perSm : 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<true>, 128, 0));  c->coopBlocksV[1] = coop ? sms * perSm : 0;
+    c->coopBlocks = c->coopBlocksV[1];
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
     delete c;

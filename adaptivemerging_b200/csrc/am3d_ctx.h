@@ -236,9 +236,8 @@ struct am3d_ctx {
   DevBuf<int> stI;     // sleeping, collection
   bool narrowTimed = false;  // events 16..19 were recorded by the last detect()
   bool evCreated = false;
-  int coopBlocksV[2][2] = {{0, 0}, {0, 0}};
+  int coopBlocksV[2] = {0, 0};  // per kernel variant: [hub support]
   int coopBlocks = 0;     // co-resident CTAs for the cooperative PGS kernel (0: cooperative launch unsupported)
-  int pgsMinB = 1;        // __launch_bounds__ min blocks per SM of the PGS kernels (register cap; AM3D_PGS_MINB)
   int usePersistent = 1;  // 0 never, 1 heuristic, 2 always (AM3D_PGS_PERSISTENT)
   long long solveLaunches = 0;
   long long kernelLaunches = 0;

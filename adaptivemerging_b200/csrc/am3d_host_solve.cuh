@@ -174,16 +174,14 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     unsigned long long* isp = c->iterState.p;
     void* args[] = {&nColors, &dcs, &dcr, &HR, &S, &dvp, &PP, &iterations, &chk, &isp};
     bool hubs = c->nHubRuns > 0;
-    int cap = c->pgsMinB == 3 ? 1 : 0;
-    const void* kfn = cap ? (hubs ? (const void*)k_pgs_persistent<3, true> : (const void*)k_pgs_persistent<3, false>)
-                          : (hubs ? (const void*)k_pgs_persistent<1, true> : (const void*)k_pgs_persistent<1, false>);
-    CK(cudaLaunchCooperativeKernel(kfn, dim3(c->coopBlocksV[cap][hubs ? 1 : 0]), dim3(128), args, 0, c->stream));
+    const void* kfn = hubs ? (const void*)k_pgs_persistent<true> : (const void*)k_pgs_persistent<false>;
+    CK(cudaLaunchCooperativeKernel(kfn, dim3(c->coopBlocksV[hubs ? 1 : 0]), dim3(128), args, 0, c->stream));
     c->kernelLaunches++;
     if (!sweep) c->solveLaunches++;
   } else {
     for (int k = 0; k < c->nColors; k++) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-      LAUNCH(c, (k_pgs_color<0, 1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+      LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
       int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
       if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 0);
     }
@@ -191,9 +189,8 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
       int last = it == iterations - 1;
       for (int k = 0; k < c->nColors; k++) {
         int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-        if (c->nHubRuns > 0) LAUNCH(c, (k_pgs_color<1, 1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
-        else if (c->pgsMinB == 3) LAUNCH(c, (k_pgs_color<1, 3, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
-        else LAUNCH(c, (k_pgs_color<1, 1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        if (c->nHubRuns > 0) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        else LAUNCH(c, (k_pgs_color<1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
         if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 1);
         if (!sweep) c->solveLaunches++;

@@ -909,8 +909,8 @@ __global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __re
   if (r < rEnd) hubReduceRun(r, H, hubDelta, dv);
 }
 
-template <int MODE, int MINB, bool HUB>
-__global__ void __launch_bounds__(128, MINB)
+template <int MODE, bool HUB>
+__global__ void __launch_bounds__(128)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
             unsigned long long* __restrict__ iterState) {
   if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
@@ -929,8 +929,8 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
 // of tiny launches become grid barriers.  Same Gauss-Seidel sequence as the per-colour launches.
 // (Measured without gain on B200, so not kept: an own split arrive/wait barrier without the L1 invalidate, L2 prefetch
 // of the next colour's records while waiting, zigzag and ticket-counter distribution of the groups: DESIGN.md.)
-template <int MINB, bool HUB>
-__global__ void __launch_bounds__(128, MINB)
+template <bool HUB>
+__global__ void __launch_bounds__(128)
 k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H,
                  SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance,
                  unsigned long long* __restrict__ iterState) {
