@@ -276,8 +276,8 @@ __device__ __forceinline__ void warmRange(const WarmCtx& W, unsigned long long k
   int lo = 0, hi = W.npSorted;
   while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] < k0) lo = mid + 1; else hi = mid; }
   rlo = lo;
-  hi = W.npSorted;
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (W.pkey0[mid] <= k0) lo = mid + 1; else hi = mid; }
+  // ranges are short here (pairs with more than 64 contacts go through the sorted index): walk to the end
+  while (lo < W.npSorted && W.pkey0[lo] == k0) lo++;
   rhi = lo;
 }
 

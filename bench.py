@@ -332,6 +332,9 @@ def main():
         "gpu_launches": int(float(tot[3])),
         "clocks": clk,
         "pgs_row_updates_per_s": float(tot[1]) / max(solve_s, 1e-12) if world == 1 else float(tot[1]) / max(solve_s, 1e-12),
+        # BASELINE.md row "PGS contact-row updates/s": 23.4 M/s (authors' Java log, tower25platform, 30 iterations, unknown CPU);
+        # body-steps/s has no published number for leaf bodies, so vs_baseline stays null
+        "pgs_row_updates_vs_baseline": (float(tot[1]) / max(solve_s, 1e-12)) / 23.4e6,
         "collections_last_step": tm.n_collections, "contacts_last_step": tm.n_contacts, "pairs_last_step": tm.n_pairs, "pgs_colors": tm.pgs_colors,
         "phase_ms_last_step": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "lcp_solve": tm.lcp_solve * 1e3,
                                "pgs_sweeps": tm.pgs_kernel_time * 1e3, "post": tm.merging * 1e3, "total": tm.compute_time * 1e3},

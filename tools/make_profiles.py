@@ -45,7 +45,10 @@ def main():
     out = [f"# Bench lines, round {tag[1:]} (B200, one fresh box per session; `tools/gpu_session_{tag}.sh`)\n",
            "Metric: body-steps/s. `resident` = state in HBM, CUDA events on the library stream; `e2e` = velocity pokes up from",
            "pinned host memory + step + full body state down into pinned host memory, every step. `roofline` = 752 B x",
-           "contacts x iterations / PGS sweep time / 6392.8 GB/s (SURVEY.md 8d); `traffic` = ncu DRAM bytes of that launch.\n",
+           "contacts x iterations / PGS sweep time / 6392.8 GB/s (SURVEY.md 8d); `traffic` = ncu DRAM bytes of that launch.",
+           "For scale: the authors' own Java log of ONE tower25platform scene (BASELINE.md) gives 7.53 ms per step = 43.6 k",
+           "leaf-body-steps/s and 23.4 M PGS row updates/s on an unknown CPU; the single-core oracle here runs the same scene at",
+           "~38 k body-steps/s and 53 M row updates/s.\n",
            "| workload | bodies/GPU | GPUs | ms/step | resident body-steps/s | e2e body-steps/s | PGS row-updates/s | roofline frac (kernel) | DRAM traffic / launch | narrowphase frac | contacts | colours |",
            "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     raw = []
@@ -80,16 +83,19 @@ def main():
     open(os.path.join(dst, f"{tag}_bench.md"), "w").write("\n".join(out) + "\n")
 
     # ncu: launch list of the default bench command + --set full summaries
-    lcsv = os.path.join(src, "launches_batch.csv")
-    if os.path.exists(lcsv):
-        shutil.copy(lcsv, os.path.join(dst, f"launches_{tag}_batch.csv"))
+    for wl, title, flags in (("batch", "default bench workload (512 x tower25platform)", ""),
+                             ("stack", "1M-box stack, merging off", " --workload stack --merging 0")):
+        lcsv = os.path.join(src, f"launches_{wl}.csv")
+        if not os.path.exists(lcsv):
+            continue
+        shutil.copy(lcsv, os.path.join(dst, f"launches_{tag}_{wl}.csv"))
         body = capture(ncu_summary.launches, lcsv)
-        head = (f"# ncu launch list, round {tag[1:]} — default bench workload (512 x tower25platform), 2 timed steps\n\n"
+        head = (f"# ncu launch list, round {tag[1:]} — {title}, 2 timed steps\n\n"
                 "Command: `AM3D_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv "
-                "python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (the profiler range is the timed region).\n"
+                f"python bench.py{flags} --steps 2 --warmup 3 --no-cpu-baseline` (the profiler range is the timed region).\n"
                 "Cold-cache, serialised launch times: compare SHARES, not absolutes. Raw CSV: "
-                f"`launches_{tag}_batch.csv`.\n\n")
-        open(os.path.join(dst, f"{tag}_ncu_launches_batch.md"), "w").write(head + body)
+                f"`launches_{tag}_{wl}.csv`.\n\n")
+        open(os.path.join(dst, f"{tag}_ncu_launches_{wl}.md"), "w").write(head + body)
     for name, title in (("full_batch", "default bench workload (512 x tower25platform per GPU)"),
                         ("full_stack", "1M-box stack, merging off")):
         rep = os.path.join(src, name + ".ncu-rep")
