@@ -36,7 +36,7 @@ def main():
     dst = os.path.join(ROOT, "profiles")
     os.makedirs(dst, exist_ok=True)
     runs = [("batch (default; config B, 512 x tower25platform per GPU, merging on)", "bench_batch", "python bench.py"),
-            ("batch, 2 GPUs (torchrun)", "bench_batch_2gpu", "torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 10 --warmup 5"),
+            ("batch, 2 GPUs (torchrun)", "bench_batch_2gpu", "torchrun --nproc-per-node 2 bench.py --gpus 2 --steps 20 --warmup 5"),
             ("stack 100^3, merging off (config M)", "bench_stack_m0", "python bench.py --workload stack --merging 0"),
             ("stack 100^3, merging on (config M)", "bench_stack_m1", "python bench.py --workload stack --merging 1"),
             ("pile 100^3, merging on (config M, jittered)", "bench_pile_m1", "python bench.py --workload pile --merging 1"),
