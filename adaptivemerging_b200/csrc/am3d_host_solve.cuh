@@ -21,7 +21,7 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
   CK(cudaMemsetAsync(c->grpDegree.p, 0, c->NS * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->counters.p + 6, 0, sizeof(int), c->stream));
-  LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, inCollection, c->grpSb1.p, c->grpSb2.p,
+  LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, gcount, inCollection, c->grpSb1.p, c->grpSb2.p,
          c->grpPrio.p, c->grpColor.p, c->grpDegree.p);
   LAUNCH(c, k_grp_hubs, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpDegree.p, c->hubMin, c->grpHubMask.p, c->counters.p + 6);
   CK(cudaMemsetAsync(c->bodyBest.p, 0, c->NS * sizeof(unsigned long long), c->stream));

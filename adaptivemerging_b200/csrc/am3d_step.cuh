@@ -492,8 +492,9 @@ __device__ __forceinline__ unsigned int hash32(unsigned int a) {
 }
 // solver bodies of a group: parent collection unless computeInCollection; negative (-1 - body) for a pinned body
 __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ parent,
-                           const int* __restrict__ flags, int inCollection, int* __restrict__ sb1, int* __restrict__ sb2,
-                           unsigned long long* __restrict__ prio, int* __restrict__ color, int* __restrict__ degree) {
+                           const int* __restrict__ flags, const int* __restrict__ gcount, int inCollection,
+                           int* __restrict__ sb1, int* __restrict__ sb2, unsigned long long* __restrict__ prio,
+                           int* __restrict__ color, int* __restrict__ degree) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   int a = gb1[g], b = gb2[g];
@@ -506,7 +507,12 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
   sb2[g] = pb ? -1 - b : b;
   if (!pa) atomicAdd(degree + a, 1);
   if (!pb) atomicAdd(degree + b, 1);
-  prio[g] = ((unsigned long long)hash32((unsigned)g) << 32) | (unsigned)(g + 1);
+  // Jones-Plassmann priority: hashed, except that long groups (sphere-tree pairs with hundreds of contacts, solved
+  // as one sequential chain) come first by size class: giants that do not touch each other then share the first
+  // colours, and a sweep costs the longest chain per colour instead of one giant per colour
+  int cnt = gcount[g];
+  unsigned long long cls = cnt > 64 ? (unsigned long long)(32 - __clz(cnt >> 6)) : 0ULL;
+  prio[g] = (cls << 59) | ((unsigned long long)(hash32((unsigned)g) >> 5) << 32) | (unsigned)(g + 1);
   color[g] = -1;
 }
 // Hubs: non-pinned solver bodies touched by >= hubMin groups (a funnel, a big merged collection).  A hub side takes
