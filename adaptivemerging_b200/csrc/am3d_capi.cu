@@ -637,6 +637,7 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   if (!name) throw AmError(AM3D_EINVAL, "null option name");
   if (!strcmp(name, "hub_min_degree")) c->hubMin = (int)value;
   else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
+  else if (!strcmp(name, "record_events")) c->recordEvents = value != 0;
   else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);
   API_END(c)
 }

@@ -198,6 +198,7 @@ struct am3d_ctx {
   DevBuf<unsigned long long> compBest;
   DevBuf<int> swB1, swB2, swCount, swStart, tmpI2, tmpI3;
   std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples
+  bool recordEvents = true; // am3d_set_option("record_events", 0): long batched runs (one device->host copy per merge step saved)
   bool recordOrders = false;
   std::vector<int> orderFull, orderSweep;
   std::vector<am3d_contact> orderFullKeys, orderSweepKeys;

@@ -267,7 +267,7 @@ static int freeSlotList(am3d_ctx* c) {
   return nfree;
 }
 static void logEvents(am3d_ctx* c, int kind, const unsigned long long* dkeys, int n) {
-  if (n <= 0) return;
+  if (n <= 0 || !c->recordEvents) return;
   std::vector<unsigned long long> k(n);
   CK(cudaMemcpyAsync(k.data(), dkeys, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));

@@ -224,6 +224,7 @@ def main():
     blob, params, desc = build_workload(args.workload, args.size, args.merging)
     nb = int((blob.a["body_type"] != 1).sum())  # non-plane leaf bodies
     sysm = RigidBodySystem(local).load(blob, params)
+    sysm.set_option("record_events", 0)  # the merge / unmerge event log is a parity-test aid
 
     def barrier():
         torch.cuda.synchronize()

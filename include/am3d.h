@@ -330,7 +330,8 @@ int am3d_download_internal_bpcs(am3d_ctx* ctx, am3d_bpc* out, int capacity, int*
 /* one RigidCollection: x[3] R[9] v[3] omega[3] mass minv jinv[9] massAngular[9] flags alive members stamp */
 int am3d_download_collection(am3d_ctx* ctx, int slot, double* out42);
 /* engine options that are not reference parameters: "hub_min_degree" (body pairs per body from which a body is a
- * hub of the contact graph, 0 = never; default 64), "pgs_persistent" (0 never / 1 heuristic / 2 always) */
+ * hub of the contact graph, 0 = never; default 64), "pgs_persistent" (0 never / 1 heuristic / 2 always),
+ * "record_events" (merge / unmerge event log for am3d_download_events, default 1; 0 saves a read-back per merge step) */
 int am3d_set_option(am3d_ctx* ctx, const char* name, double value);
 int am3d_mark(am3d_ctx* ctx, int slot);
 int am3d_elapsed_ms(am3d_ctx* ctx, double* ms);
