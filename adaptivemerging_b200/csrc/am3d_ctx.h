@@ -148,7 +148,7 @@ struct am3d_ctx {
 
   // ---- shapes [NSH] ---------------------------------------------------------------------------
   DevBuf<int> shType, shBody, shRoot, shLarge;
-  DevBuf<double> shSize, shRadius, shP, shLR, shLt, shX, shR, shBoundC, shBoundR;  // shX/shR: world transform this step
+  DevBuf<double> shSize, shRadius, shP, shLR, shLt, shX, shR, shBoundC, shBoundR, shBoundH;  // shX/shR: world transform this step
   // ---- sphere-tree nodes [NN] -------------------------------------------------------------------
   DevBuf<double> ndC, ndR;
   DevBuf<int> ndFirst, ndCount, ndRank;

@@ -18,10 +18,11 @@
 // ------------------------------------------------------------------------------------------------
 __global__ void k_shape_update(int nsh, const int* __restrict__ shType, const int* __restrict__ shBody,
                                const int* __restrict__ shRoot, const double* __restrict__ shRadius,
-                               const double* __restrict__ shLR, const double* __restrict__ shLt,
+                               const double* __restrict__ shSize, const double* __restrict__ shLR, const double* __restrict__ shLt,
                                const int* __restrict__ btype, const double* __restrict__ x, const double* __restrict__ R,
                                const double* __restrict__ ndC, const double* __restrict__ ndR, double* __restrict__ shX,
-                               double* __restrict__ shR, double* __restrict__ shBoundC, double* __restrict__ shBoundR) {
+                               double* __restrict__ shR, double* __restrict__ shBoundC, double* __restrict__ shBoundR,
+                               double* __restrict__ shBoundH) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nsh) return;
   int b = shBody[s];
@@ -38,16 +39,24 @@ __global__ void k_shape_update(int nsh, const int* __restrict__ shType, const in
   stm(shR + 9 * s, T.R);
   st3(shX + 3 * s, T.t);
   int t = shType[s];
+  // bounding sphere (grid cell size, plane tests) and world AABB half extents (pair filter)
   if (t == AM3D_SHAPE_BOX) {
     st3(shBoundC + 3 * s, T.t);
     shBoundR[s] = shRadius[s];
+    d3 h = vscale(0.5, ld3(shSize + 3 * s));
+    const m3& A = T.R;
+    st3(shBoundH + 3 * s, d3(fabs(A.m[0]) * h.x + fabs(A.m[1]) * h.y + fabs(A.m[2]) * h.z,
+                             fabs(A.m[3]) * h.x + fabs(A.m[4]) * h.y + fabs(A.m[5]) * h.z,
+                             fabs(A.m[6]) * h.x + fabs(A.m[7]) * h.y + fabs(A.m[8]) * h.z));
   } else if (t == AM3D_SHAPE_TREE) {
     int root = shRoot[s];
     st3(shBoundC + 3 * s, xfP(T, ld3(ndC + 3 * root)));
     shBoundR[s] = ndR[root];
+    st3(shBoundH + 3 * s, d3(ndR[root], ndR[root], ndR[root]));
   } else {
     st3(shBoundC + 3 * s, d3());
     shBoundR[s] = 0;
+    st3(shBoundH + 3 * s, d3());
   }
 }
 
@@ -93,6 +102,7 @@ struct PairCtx {
   const long long* stamp;
   const double* bc;
   const double* br;
+  const double* bh;
   unsigned long long* pairKey;
   unsigned long long* pairVal;
   int* counter;
@@ -133,9 +143,13 @@ __device__ __forceinline__ void tryPair(const PairCtx& C, int sa, int sb) {
   C.pairVal[idx] = ((unsigned long long)(unsigned)first << 32) | (unsigned)second;
 }
 
-__device__ __forceinline__ bool sphereBoxOverlap(const d3& ca, double ra, const d3& cb, double rb) {
-  double r = ra + rb;
-  return fabs(ca.x - cb.x) <= r && fabs(ca.y - cb.y) <= r && fabs(ca.z - cb.z) <= r;
+// World AABBs (boxes: |R| h, trees: the root sphere's cube) with a margin far above rounding error: boxes whose AABBs
+// are apart are disjoint, so the reference's own tests (bounding spheres, then the 15-axis SAT; root-sphere tests for
+// trees) return no contact for them -- the filter never changes a contact set.
+__device__ __forceinline__ bool aabbOverlap(const d3& ca, const d3& ha, const d3& cb, const d3& hb) {
+  const double rel = 1.0 + 1e-12, abs_ = 1e-9;
+  return fabs(ca.x - cb.x) <= (ha.x + hb.x) * rel + abs_ && fabs(ca.y - cb.y) <= (ha.y + hb.y) * rel + abs_ &&
+         fabs(ca.z - cb.z) <= (ha.z + hb.z) * rel + abs_;
 }
 
 // one thread per small shape: its own cell (partners with a larger shape id) and the 13 neighbouring cells of the
@@ -145,8 +159,7 @@ __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys,
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int s = vals[i];
-  d3 c = ld3(C.bc + 3 * s);
-  double r = C.br[s];
+  d3 c = ld3(C.bc + 3 * s), h = ld3(C.bh + 3 * s);
   int sc = C.scene[C.shBody[s]];
   int ix = cellCoord(c.x, inv), iy = cellCoord(c.y, inv), iz = cellCoord(c.z, inv);
   for (int dz = -1; dz <= 1; dz++)
@@ -165,7 +178,7 @@ __global__ void k_pairs_grid(int n, const unsigned long long* __restrict__ keys,
         for (int j = lo; j < n && keys[j] == k; j++) {
           int t = vals[j];
           if (own && t <= s) continue;
-          if (!sphereBoxOverlap(c, r, ld3(C.bc + 3 * t), C.br[t])) continue;
+          if (!aabbOverlap(c, h, ld3(C.bc + 3 * t), ld3(C.bh + 3 * t))) continue;
           tryPair(C, s, t);
         }
       }
@@ -180,14 +193,14 @@ __global__ void k_pairs_special(int nsh, const int* __restrict__ shType, const i
   if (t >= nsh) return;
   int ty = shType[t];
   if (ty == AM3D_SHAPE_PLANE) return;
-  d3 c = ld3(C.bc + 3 * t);
+  d3 c = ld3(C.bc + 3 * t), hh = ld3(C.bh + 3 * t);
   double r = C.br[t];
   int sc = C.scene[C.shBody[t]];
   for (int k = largeStart[sc]; k < largeStart[sc + 1]; k++) {
     int l = largeList[k];
     if (l == t) continue;
     if (shLarge[t] && t < l) continue;  // large-large pairs once
-    if (!sphereBoxOverlap(c, r, ld3(C.bc + 3 * l), C.br[l])) continue;
+    if (!aabbOverlap(c, hh, ld3(C.bc + 3 * l), ld3(C.bh + 3 * l))) continue;
     tryPair(C, t, l);
   }
   for (int k = planeStart[sc]; k < planeStart[sc + 1]; k++) {

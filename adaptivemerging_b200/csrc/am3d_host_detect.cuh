@@ -6,8 +6,8 @@
 static void detect(am3d_ctx* c) {
   int nsh = c->NSH;
   std::swap(c->cur, c->prev);  // ContactPool.swapPools (ContactPool.java:60-65): last step's contacts stay readable
-  LAUNCH(c, k_shape_update, nblk(nsh), BLK, nsh, c->shType.p, c->shBody.p, c->shRoot.p, c->shRadius.p, c->shLR.p, c->shLt.p,
-         c->btype.p, c->x.p, c->R.p, c->ndC.p, c->ndR.p, c->shX.p, c->shR.p, c->shBoundC.p, c->shBoundR.p);
+  LAUNCH(c, k_shape_update, nblk(nsh), BLK, nsh, c->shType.p, c->shBody.p, c->shRoot.p, c->shRadius.p, c->shSize.p, c->shLR.p, c->shLt.p,
+         c->btype.p, c->x.p, c->R.p, c->ndC.p, c->ndR.p, c->shX.p, c->shR.p, c->shBoundC.p, c->shBoundR.p, c->shBoundH.p);
   double inv = 1.0 / c->cellSize;
   if (c->pairKey.cap == 0) {
     size_t cap = (size_t)nsh * 8 + 1024;
@@ -24,7 +24,7 @@ static void detect(am3d_ctx* c) {
   int np = 0;
   for (int attempt = 0; attempt < 3; attempt++) {
     CK(cudaMemsetAsync(c->counters.p, 0, sizeof(int), c->stream));
-    PairCtx PC{c->shBody.p, c->bShapeFirst.p, c->parent.p, c->flags.p, c->scene.p, c->stamp.p, c->shBoundC.p, c->shBoundR.p,
+    PairCtx PC{c->shBody.p, c->bShapeFirst.p, c->parent.p, c->flags.p, c->scene.p, c->stamp.p, c->shBoundC.p, c->shBoundR.p, c->shBoundH.p,
                c->pairKey.p, c->pairVal.p, c->counters.p, (int)std::min<size_t>(c->pairKey.cap, 0x7fffffff),
                bitsFor((unsigned long long)c->NB), c->haveComposites ? 16 : 0};
     if (c->nSmall > 0)

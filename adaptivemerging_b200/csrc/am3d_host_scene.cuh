@@ -98,7 +98,7 @@ static void resetState(am3d_ctx* c) {
   h2dv(c, c->shType, H.shape_type); h2dv(c, c->shBody, H.shape_body); h2dv(c, c->shRoot, H.shape_root);
   h2dv(c, c->shSize, H.shape_size); h2dv(c, c->shRadius, H.shape_radius); h2dv(c, c->shP, H.shape_p);
   h2dv(c, c->shLR, H.shape_lR); h2dv(c, c->shLt, H.shape_lt);
-  c->shX.ensure(3 * H.nsh); c->shR.ensure(9 * H.nsh); c->shBoundC.ensure(3 * H.nsh); c->shBoundR.ensure(H.nsh);
+  c->shX.ensure(3 * H.nsh); c->shR.ensure(9 * H.nsh); c->shBoundC.ensure(3 * H.nsh); c->shBoundR.ensure(H.nsh); c->shBoundH.ensure(3 * H.nsh);
   h2dv(c, c->ndC, H.node_c); h2dv(c, c->ndR, H.node_r); h2dv(c, c->ndFirst, H.node_first);
   h2dv(c, c->ndCount, H.node_count); h2dv(c, c->ndRank, H.node_rank);
   // broadphase classes: planes / large shapes (tested against everything) / small shapes (grid)
