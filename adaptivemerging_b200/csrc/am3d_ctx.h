@@ -5,6 +5,9 @@
 // live in a "solver body" index space [0,NB) = leaf bodies in XML parse order, [NB, NB+NCcap) =
 // RigidCollection slots, so that the PGS kernels address a merged collection exactly like a free body.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #define DVS 8  // deltaV stride in doubles: 6 used, padded so that a body is two aligned 32-byte accesses
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,6 +29,10 @@ struct AmError {
   AmError(int c, const std::string& m) : code(c), msg(m) {}
 };
 
+// stream of the context whose API call is running on this thread (set by API_BEGIN)
+inline cudaStream_t& amCurrentStream() { static thread_local cudaStream_t s = nullptr; return s; }
+inline size_t& amAllocatedBytes() { static size_t b = 0; return b; }  // device bytes handed out by DevBuf (all contexts)
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -39,13 +46,23 @@ struct DevBuf {
     return *this;
   }
   ~DevBuf() { if (p) cudaFree(p); }
+  // Growth goes through the stream-ordered allocator on the calling context's stream: cudaFree / cudaMalloc in the
+  // middle of a run cost 10-200 ms each on B200 (measured), cudaMallocAsync / cudaFreeAsync from the retained pool
+  // (release threshold = max, set in am3d_create) cost microseconds and need no device-wide synchronisation.
   void ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
-    size_t ncap = n + n / 2 + 256;  // regrowth costs a cudaMalloc + cudaFree (device-wide syncs): grow geometrically
+    size_t ncap = n + n / 2 + 256;  // grow geometrically
+    cudaStream_t s = st ? st : amCurrentStream();
     T* q = nullptr;
-    CK(cudaMalloc(&q, ncap * sizeof(T)));
-    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, st));
-    if (p) { CK(cudaStreamSynchronize(st)); cudaFree(p); }
+    static const bool traceAlloc = getenv("AM3D_TRACE_ALLOC") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    CK(cudaMallocAsync(&q, ncap * sizeof(T), s));
+    if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (p) CK(cudaFreeAsync(p, s));  // ordered after everything already queued on the stream that uses p
+    if (traceAlloc)
+      fprintf(stderr, "[am3d alloc] %.1f MB (was %.1f MB): %.3f ms\n", ncap * sizeof(T) / 1e6, cap * sizeof(T) / 1e6,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    amAllocatedBytes() += (ncap - cap) * sizeof(T);
     p = q;
     cap = ncap;
   }
