@@ -39,6 +39,9 @@ final class AM3DNative implements AutoCloseable {
     private static final MethodHandle NUM_BODIES = h("am3d_num_bodies", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle DOWNLOAD_BODIES = h("am3d_download_bodies",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle DOWNLOAD_BODIES_ASYNC = h("am3d_download_bodies_async",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle WAIT_DOWNLOAD = h("am3d_wait_download", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle NUM_CONTACTS = h("am3d_num_contacts", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
     private static final MethodHandle DOWNLOAD_CONTACTS = h("am3d_download_contacts",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS));
@@ -90,6 +93,11 @@ final class AM3DNative implements AutoCloseable {
     void downloadBodies(MemorySegment x, MemorySegment R, MemorySegment v, MemorySegment w, MemorySegment sleeping, MemorySegment collection) {
         try { check((int) DOWNLOAD_BODIES.invokeExact(ctx, x, R, v, w, sleeping, collection)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }
     }
+    /** same read, copied out on a second stream while the next step runs; valid after waitDownload() (draw one frame behind) */
+    void downloadBodiesAsync(MemorySegment x, MemorySegment R, MemorySegment v, MemorySegment w, MemorySegment sleeping, MemorySegment collection) {
+        try { check((int) DOWNLOAD_BODIES_ASYNC.invokeExact(ctx, x, R, v, w, sleeping, collection)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); }
+    }
+    void waitDownload() { try { check((int) WAIT_DOWNLOAD.invokeExact(ctx)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     /** out: capacity x am3d_contact; returns the number written */
     int downloadContacts(MemorySegment out, int capacity, boolean includeInternal) {
         MemorySegment n = arena.allocate(JAVA_INT);
