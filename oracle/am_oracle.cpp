@@ -16,7 +16,10 @@
 //  * options marked unsupported in include/am3d.h (shuffle, post-stabilisation, cycle merge
 //    condition, position-level metric, collection BVH, Coriolis) are not restated;
 //  * an external Gauss-Seidel order can be supplied for either solve so that the CUDA path's
-//    colour order can be replayed (north_star parity mode 2).
+//    colour order can be replayed (north_star parity mode 2); when that order marks hub sides
+//    (bodies the CUDA path updates Jacobi-style across the groups of one colour) the
+//    replay follows the same scheme (pgsSolveHub) -- without such marks the solve is the reference's
+//    plain sequential Gauss-Seidel.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
