@@ -512,25 +512,32 @@ struct ContactOut {
   double *pW, *nW, *t1W, *t2W, *pB1, *nB1, *t1B1, *t2B1, *viol, *prevViol, *lam, *lamWarm;
 };
 
-__global__ void k_contact_set(int np, const int* __restrict__ bShapeFirst,
+// owner[c] = the candidate pair that emitted contact c (canonical order): lets k_contact_set run one thread per
+// CONTACT, so that every store of the ~50 it does per contact is coalesced across the warp
+__global__ void k_contact_owner(int np, const int* __restrict__ pairCount, const int* __restrict__ pairOut, int* __restrict__ owner) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  int n = pairCount[i], out = pairOut[i];
+  for (int k = 0; k < n; k++) owner[out + k] = i;
+}
+
+__global__ void k_contact_set(int nc, const int* __restrict__ owner, const int* __restrict__ bShapeFirst,
                               const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairSlot,
-                              const int* __restrict__ pairCount, const int* __restrict__ pairOut,
+                              const int* __restrict__ pairOut,
                               const int* __restrict__ shBody, const double* __restrict__ x, const double* __restrict__ R,
                               const double* __restrict__ hitPos, const double* __restrict__ hitNrm,
                               const double* __restrict__ hitViol, const int* __restrict__ hitMeta, ContactOut O) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= np) return;
-  int n = pairCount[i];
-  if (n == 0) return;
+  int out = blockIdx.x * blockDim.x + threadIdx.x;
+  if (out >= nc) return;
+  int i = owner[out];
   int s1 = (int)(pairVal[i] >> 32), s2 = (int)(pairVal[i] & 0xffffffffu);
   int b1 = shBody[s1], b2 = shBody[s2];  // composite parts report their parent (Contact.java:169-180)
   xf T1;
   T1.R = ldm(R + 9 * b1);
   T1.t = ld3(x + 3 * b1);
   unsigned long long k0 = pairKey0(shBody, bShapeFirst, s1, s2);
-  long long slot = pairSlot[i];
-  int out = pairOut[i];
-  for (int k = 0; k < n; k++, slot++, out++) {
+  long long slot = (long long)pairSlot[i] + (out - pairOut[i]);
+  {
     int4 m = reinterpret_cast<const int4*>(hitMeta)[slot];
     d3 p = ld3(hitPos + 3 * slot), nW = ld3(hitNrm + 3 * slot);
     double anx = fabs(nW.x), any = fabs(nW.y), anz = fabs(nW.z);

@@ -81,8 +81,12 @@ static void detect(am3d_ctx* c) {
                   c->cur.state.p, c->cur.isNew.p, c->cur.key0.p, c->cur.key1.p, c->cur.pW.p, c->cur.nW.p, c->cur.t1W.p,
                   c->cur.t2W.p, c->cur.pB1.p, c->cur.nB1.p, c->cur.t1B1.p, c->cur.t2B1.p, c->cur.viol.p, c->cur.prevViol.p,
                   c->cur.lam.p, c->cur.lamWarm.p};
-    LAUNCH(c, k_contact_set, nblk(np, 128), 128, np, c->bShapeFirst.p, c->pairValSorted.p, c->pairSlot.p, c->pairCount.p,
-           c->pairOut.p, c->shBody.p, c->x.p, c->R.p, c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p, CO);
+    if (nc > 0) {
+      c->tmpI3.ensure(nc + 1);
+      LAUNCH(c, k_contact_owner, nblk(np), BLK, np, c->pairCount.p, c->pairOut.p, c->tmpI3.p);
+      LAUNCH(c, k_contact_set, nblk(nc, 128), 128, nc, c->tmpI3.p, c->bShapeFirst.p, c->pairValSorted.p, c->pairSlot.p, c->pairOut.p,
+             c->shBody.p, c->x.p, c->R.p, c->hitPos.p, c->hitNrm.p, c->hitViol.p, c->hitMeta.p, CO);
+    }
   }
   c->cur.n = nc;
   c->cur.nSorted = nc;
