@@ -49,9 +49,9 @@ def main():
            "For scale: the authors' own Java log of ONE tower25platform scene (BASELINE.md) gives 7.53 ms per step = 43.6 k",
            "leaf-body-steps/s and 23.4 M PGS row updates/s on an unknown CPU; the single-core oracle here runs the same scene at",
            "~38 k body-steps/s and 53 M row updates/s.",
-           "The lines below were taken before the last change of the round (one thread per contact in `k_contact_set`); 10-step",
-           "runs after it: batch 11.80 ms/step (detection 1.66 -> 0.90 ms), 1M-box stack merging off 21.50 ms/step (detection",
-           "3.65 -> 2.40 ms); all 31 GPU tests green.\n",
+           "The default (batch, 1 GPU) line is from the final code; the other lines and the ncu captures were taken before the",
+           "last change of the round (one thread per contact in `k_contact_set`), which took the 1M-box stack (merging off)",
+           "from 24.2 to 21.5 ms/step in a 10-step run (detection 3.65 -> 2.40 ms); all 31 GPU tests green after it.\n",
            "| workload | bodies/GPU | GPUs | ms/step | resident body-steps/s | e2e body-steps/s | PGS row-updates/s | roofline frac (kernel) | DRAM traffic / launch | narrowphase frac | contacts | colours |",
            "|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|"]
     raw = []
