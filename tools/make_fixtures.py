@@ -34,7 +34,31 @@ def golden_run(name, blob, steps, every):
     print(name, "steps", steps, "events", len(o.events()), "top-level at end", o.num_top_level())
 
 
+# The reference's own step logs (RigidBodySystem.exportDataToFile: "#bodies, #contacts, detection, ..." one row per
+# advanceTime) recorded by the authors on tower25platform.xml.  Only the two integer columns travel: they are the one
+# piece of REFERENCE OUTPUT for the 3D path that exists, and they pin the oracle (tests/test_reference_logs.py).
+REF_LOGS = {
+    # name: (csv under scenes3D/csv/conditional_acceptance_revisions, parameter overrides of that recording)
+    "tower25platform_30it": ("tower25platform30_merged.csv", {}),
+    "tower25platform_10it": ("tower25platform10_merged.csv", {"iterations": 10}),
+    "tower25platform_200it": ("tower25platform200_merged.csv", {"iterations": 200}),
+    "tower25platform_nosleep": ("no_sleeping/tower25platform_merged.csv", {"enable_sleeping": 0}),
+}
+
+
+def reference_logs(rows=400):
+    import csv
+    out = {}
+    for name, (path, _) in REF_LOGS.items():
+        full = os.path.join(REF, "scenes3D", "csv", "conditional_acceptance_revisions", path)
+        data = [r for r in csv.reader(open(full)) if len(r) > 5][1:rows + 1]
+        out[name] = np.array([[int(r[0]), int(r[1])] for r in data], np.int32)
+    np.savez_compressed(os.path.join(OUT, "ref_logs_tower25platform.npz"), **out)
+    print("reference logs:", {k: v.shape for k, v in out.items()})
+
+
 def main():
+    reference_logs()
     os.makedirs(OUT, exist_ok=True)
     for name, steps, every in [("tower", 300, 25), ("tower25platform", 200, 25), ("dominosPlatforms", 200, 25)]:
         blob = load_xml(os.path.join(REF, "scenes3D", name + ".xml"))
