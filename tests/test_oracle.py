@@ -66,3 +66,30 @@ def test_mixed_scene_runs(oracle_lib):
     # tree x tree, tree x plane / box x tree and box pairs all occurred
     assert len(seen) >= 3
     assert np.isfinite(o.bodies()["x"]).all()
+
+
+def test_config_d_dominos_cascade():
+    """SURVEY.md 8d config D (paper Fig. 7): dominosPlatforms.xml, 600 steps to let the 99 dominos merge with their
+    three sprung platforms, then the scripted push that replaces the README's mouse drag (omega = (0, 0, -2) on
+    domino66, the leftmost domino of the top platform), 1400 more steps."""
+    from adaptivemerging_b200.ctypes_defs import apply_overrides, default_params
+    from oracle.oracle import Oracle
+    from tests.util import golden_scene
+    blob = golden_scene("dominosPlatforms")
+    o = Oracle(blob, apply_overrides(default_params(), blob.overrides))
+    for _ in range(600):
+        o.step(0.05)
+    ev = o.events()
+    assert o.timings().n_bodies == 4 and o.timings().n_contacts == 0      # 3 platform collections + the plane
+    assert (ev[:, 1] == 0).sum() == 99 and (ev[:, 1] == 1).sum() == 0     # every domino merged, nothing unmerged yet
+    n0 = len(ev)
+    o.add_body_velocity(blob.names.index("domino66"), domega=np.array([0.0, 0.0, -2.0]))
+    for _ in range(100):
+        o.step(0.05)
+    ev = o.events()
+    assert (ev[n0:, 1] == 1).sum() >= 60 and o.timings().n_bodies >= 60   # the push unmerges the top platform's row
+    for _ in range(1300):
+        o.step(0.05)
+    ev = o.events()
+    assert (ev[n0:, 1] == 0).sum() >= 300 and (ev[n0:, 1] == 1).sum() >= 300   # the cascade: unmerge / re-merge waves
+    assert o.timings().n_bodies <= 6                                           # everything comes to rest merged again
