@@ -19,7 +19,7 @@ EXPORTS = [
     "am3d_download_deltav", "am3d_set_lambdas", "am3d_stats", "am3d_download_solve_order", "am3d_mark", "am3d_elapsed_ms",
     "am3d_num_events", "am3d_download_events", "am3d_record_orders", "am3d_download_order", "am3d_num_internal_bpcs",
     "am3d_download_internal_bpcs", "am3d_download_collection", "am3d_set_option", "am3d_add_velocities",
-    "am3d_download_bodies_async", "am3d_wait_download",
+    "am3d_download_bodies_async", "am3d_wait_download", "am3d_download_list_order",
 ]
 
 _LIB = None

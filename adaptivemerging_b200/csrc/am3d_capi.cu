@@ -82,17 +82,16 @@ static void snapshotOrder(am3d_ctx* c, int which) {
   if (which) fetchContacts(c, c->icon, c->icon.n, in.data(), 1);
   // per solve position: dense colour index and hub sides of the group the contact belongs to
   int ng = c->nGroups;
-  std::vector<int> sgStart(ng), sgCount(ng), sgFlags(ng), sgBpc(ng), gcol(ng);
+  std::vector<int> sgStart(ng), sgCount(ng), sgFlags(ng), sgPhase(ng);
   CK(cudaMemcpy(sgStart.data(), c->sgStart.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(sgCount.data(), c->sgCount.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(sgFlags.data(), c->sgFlags.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(sgBpc.data(), c->sgBpc.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(gcol.data(), c->grpColor.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(sgPhase.data(), c->sgPhase.p, ng * sizeof(int), cudaMemcpyDeviceToHost));
   std::vector<int> posColor(n, 0), posHub(n, 0);
   for (int p = 0; p < ng; p++)
     for (int k = 0; k < sgCount[p]; k++) {
       int idx = sgStart[p] + k;
-      if (idx < n) { posColor[idx] = c->colorDense[gcol[sgBpc[p]]]; posHub[idx] = ((sgFlags[p] & SG_HUB1) ? 1 : 0) | ((sgFlags[p] & SG_HUB2) ? 2 : 0); }
+      if (idx < n) { posColor[idx] = sgPhase[p]; posHub[idx] = ((sgFlags[p] & SG_HUB1) ? 1 : 0) | ((sgFlags[p] & SG_HUB2) ? 2 : 0); }
     }
   dst.resize(n);
   for (int k = 0; k < n; k++) {
@@ -215,14 +214,15 @@ static void stepOnce(am3d_ctx* c, double dt) {
   c->T.warmstart = evMs(c, 2, 3) * 1e-3;
   c->T.update_collections = swept ? evMs(c, 3, 14) * 1e-3 : 0;
   c->T.single_it_pgs = swept ? evMs(c, 8, 9) * 1e-3 : 0;
-  c->T.contact_ordering = 0;
+  c->T.contact_ordering = (swept && c->orderingTimed) ? evMs(c, 20, 21) * 1e-3 : 0;
+  c->orderingTimed = false;
   c->T.unmerging = evMs(c, 14, 4) * 1e-3;
   c->T.lcp_solve = evMs(c, 4, 5) * 1e-3;
   c->T.merging = evMs(c, 6, 15) * 1e-3;
   c->T.merging_build = c->T.merging;
   c->T.unmerging_build = c->T.unmerging;
   c->T.compute_time = evMs(c, 0, 7) * 1e-3;
-  c->T.n_bodies = NB;
+  c->T.n_bodies = NB - c->nMergedLeaves + c->nCollections;  // bodies.size(): a collection counts as one (RigidBodySystem.java:503)
   c->T.n_contacts = c->cur.n;  // collision.contacts.size() at the end of the step, unmerge-appended contacts included
   c->T.n_collections = c->nCollections;
 }
@@ -231,11 +231,19 @@ static void stepOnce(am3d_ctx* c, double dt) {
 // C ABI
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
+static void waitPending(am3d_ctx* c) {
+  if (c->pending.valid()) {
+    int rc = c->pending.get();
+    if (rc != AM3D_OK && c->asyncStatus == AM3D_OK) c->asyncStatus = rc;
+  }
+}
 #define API_BEGIN(ctx)                      \
   if (!(ctx)) return AM3D_EINVAL;           \
   try {                                     \
+    waitPending(ctx);                       \
     cudaSetDevice((ctx)->device);           \
-    amCurrentStream() = (ctx)->stream;
+    amCurrentStream() = (ctx)->stream;      \
+    amCurrentPool() = (ctx)->pool;
 #define API_END(ctx)                        \
     return AM3D_OK;                         \
   } catch (const AmError& e) {              \
@@ -247,7 +255,6 @@ static void stepOnce(am3d_ctx* c, double dt) {
   }
 
 static void checkParams(const am3d_params* p) {
-  if (p->update_contacts_in_collections && !p->organize_contacts) throw AmError(AM3D_EUNSUPPORTED, "organize_contacts = false is not supported");
   if (p->shuffle) throw AmError(AM3D_EUNSUPPORTED, "shuffle is not supported");
   if (p->enable_post_stabilization) throw AmError(AM3D_EUNSUPPORTED, "post-stabilisation is not supported");
   if (p->collection_cd != 0) throw AmError(AM3D_EUNSUPPORTED, "only the brute-force collection collision mode is supported");
@@ -290,13 +297,19 @@ int am3d_create(int device, am3d_ctx** out) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     amCurrentStream() = c->stream;
-    {  // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
-      cudaMemPool_t pool;
-      CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    {  // a private pool that keeps freed blocks instead of returning them to the driver at every synchronisation
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      CK(cudaMemPoolCreate(&c->pool, &props));
       unsigned long long keep = ~0ULL;
-      CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      CK(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+      amCurrentPool() = c->pool;
     }
-    for (int i = 0; i < 20; i++) CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 24; i++) CK(cudaEventCreate(&c->ev[i]));
     c->evCreated = true;
     am3d_default_params(&c->P);
     int coop = 0, sms = 0, perSm = 0;
@@ -306,9 +319,12 @@ int am3d_create(int device, am3d_ctx** out) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<false>, 128, 0)); c->coopBlocksV[0] = coop ? sms * perSm : 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<true>, 128, 0));  c->coopBlocksV[1] = coop ? sms * perSm : 0;
     c->coopBlocks = c->coopBlocksV[1];
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_layers, 256, 0)); c->bfsBlocks = coop ? sms * perSm : 0;
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
+    cudaMemPool_t pool = c->pool;
     delete c;
+    if (pool) cudaMemPoolDestroy(pool);
     return e.code;
   }
   *out = c;
@@ -317,16 +333,20 @@ int am3d_create(int device, am3d_ctx** out) {
 
 int am3d_destroy(am3d_ctx* c) {
   if (!c) return AM3D_EINVAL;
+  waitPending(c);
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->evCreated) for (int i = 0; i < 20; i++) cudaEventDestroy(c->ev[i]);
+  if (c->evCreated) for (int i = 0; i < 24; i++) cudaEventDestroy(c->ev[i]);
   if (c->copyStream) {
     cudaStreamSynchronize(c->copyStream);
     cudaEventDestroy(c->evSnap); cudaEventDestroy(c->evCopied);
     cudaStreamDestroy(c->copyStream);
   }
   if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
+  cudaMemPool_t pool = c->pool;
+  delete c;  // frees every device buffer
+  if (pool) cudaMemPoolDestroy(pool);
+  if (amCurrentPool() == pool) amCurrentPool() = nullptr;
   return AM3D_OK;
 }
 
@@ -342,7 +362,7 @@ int am3d_upload_scene(am3d_ctx* c, const am3d_scene* s) {
      // go back to the driver for memory stalls the step by ~100 ms
     size_t warm = std::max<size_t>((amAllocatedBytes() - before) / 2, 64u << 20);
     void* tmp = nullptr;
-    if (cudaMallocAsync(&tmp, warm, c->stream) == cudaSuccess) cudaFreeAsync(tmp, c->stream);
+    if (cudaMallocFromPoolAsync(&tmp, warm, c->pool, c->stream) == cudaSuccess) cudaFreeAsync(tmp, c->stream);
     else cudaGetLastError();
     CK(cudaStreamSynchronize(c->stream));
   }
@@ -376,15 +396,37 @@ int am3d_step(am3d_ctx* c, double dt, int nsteps) {
   for (int i = 0; i < nsteps; i++) stepOnce(c, dt);
   API_END(c)
 }
-int am3d_step_async(am3d_ctx* c, double dt, int nsteps) { return am3d_step(c, dt, nsteps); }
+static int stepBody(am3d_ctx* c, double dt, int nsteps) {
+  try {
+    cudaSetDevice(c->device);
+    amCurrentStream() = c->stream;
+    amCurrentPool() = c->pool;
+    for (int i = 0; i < nsteps; i++) stepOnce(c, dt);
+    return AM3D_OK;
+  } catch (const AmError& e) {
+    c->lastError = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    c->lastError = e.what();
+    return AM3D_ECUDA;
+  }
+}
+int am3d_step_async(am3d_ctx* c, double dt, int nsteps) {
+  API_BEGIN(c)  // waits for steps still pending from an earlier call
+  if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
+  if (c->asyncStatus != AM3D_OK) { int rc = c->asyncStatus; c->asyncStatus = AM3D_OK; return rc; }
+  c->pending = std::async(std::launch::async, stepBody, c, dt, nsteps);
+  API_END(c)
+}
 int am3d_sync(am3d_ctx* c) {
   API_BEGIN(c)
   CK(cudaStreamSynchronize(c->stream));
+  if (c->asyncStatus != AM3D_OK) { int rc = c->asyncStatus; c->asyncStatus = AM3D_OK; return rc; }
   API_END(c)
 }
 
 int am3d_num_bodies(const am3d_ctx* c) { return c ? c->NB : AM3D_EINVAL; }
-int am3d_total_steps(const am3d_ctx* c) { return c ? c->totalSteps : AM3D_EINVAL; }
+int am3d_total_steps(const am3d_ctx* c) { if (c) waitPending(const_cast<am3d_ctx*>(c)); return c ? c->totalSteps : AM3D_EINVAL; }
 
 // Outbound read of the body state (what Display reads after a step).  The state is snapshot into staging buffers on
 // the step's stream and copied to the host on a second stream, so that with the _async form the copy of step N runs
@@ -500,6 +542,7 @@ int am3d_add_velocities(am3d_ctx* c, const double* dv, const double* domega) {
 
 int am3d_num_contacts(am3d_ctx* c, int include_internal) {
   if (!c) return AM3D_EINVAL;
+  waitPending(c);
   return c->cur.n + (include_internal ? c->icon.n : 0);
 }
 
@@ -517,7 +560,7 @@ int am3d_download_contacts(am3d_ctx* c, am3d_contact* out, int capacity, int inc
 }
 
 // merge / unmerge decisions so far: (step, kind 0 = pair became internal / 1 = pair left a collection, bodyLo, bodyHi)
-int am3d_num_events(am3d_ctx* c) { return c ? (int)(c->events.size() / 4) : AM3D_EINVAL; }
+int am3d_num_events(am3d_ctx* c) { if (c) waitPending(c); return c ? (int)(c->events.size() / 4) : AM3D_EINVAL; }
 int am3d_download_events(am3d_ctx* c, int32_t* out, int capacity, int* count) {
   API_BEGIN(c)
   int n = std::min((int)(c->events.size() / 4), capacity);
@@ -543,7 +586,7 @@ int am3d_download_order(am3d_ctx* c, int which, am3d_contact* out, int capacity,
   API_END(c)
 }
 
-int am3d_num_bpcs(am3d_ctx* c) { return c ? c->bpPrev.n : AM3D_EINVAL; }
+int am3d_num_bpcs(am3d_ctx* c) { if (c) waitPending(c); return c ? c->bpPrev.n : AM3D_EINVAL; }
 int am3d_download_bpcs(am3d_ctx* c, am3d_bpc* out, int capacity, int* count) {
   API_BEGIN(c)
   int n = std::min(c->bpPrev.n, capacity);
@@ -567,7 +610,7 @@ int am3d_download_bpcs(am3d_ctx* c, am3d_bpc* out, int capacity, int* count) {
   API_END(c)
 }
 
-int am3d_num_internal_bpcs(am3d_ctx* c) { return c ? c->ibp.n : AM3D_EINVAL; }
+int am3d_num_internal_bpcs(am3d_ctx* c) { if (c) waitPending(c); return c ? c->ibp.n : AM3D_EINVAL; }
 int am3d_download_internal_bpcs(am3d_ctx* c, am3d_bpc* out, int capacity, int* count) {
   API_BEGIN(c)
   int n = std::min(c->ibp.n, capacity);
@@ -590,6 +633,7 @@ int am3d_download_internal_bpcs(am3d_ctx* c, am3d_bpc* out, int capacity, int* c
 
 int am3d_get_timings(am3d_ctx* c, am3d_timings* t) {
   if (!c || !t) return AM3D_EINVAL;
+  waitPending(c);
   *t = c->T;
   return AM3D_OK;
 }
@@ -645,6 +689,7 @@ int am3d_download_solve_order(am3d_ctx* c, int32_t* order, int capacity, int* co
 
 int am3d_stats(am3d_ctx* c, double* out /* [4]: kernel launches, solve launches, row updates, solve kernel seconds */) {
   if (!c || !out) return AM3D_EINVAL;
+  waitPending(c);
   out[0] = (double)c->kernelLaunches; out[1] = (double)c->solveLaunches; out[2] = c->rowUpdates; out[3] = c->solveSeconds;
   return AM3D_OK;
 }
@@ -655,6 +700,7 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   if (!strcmp(name, "hub_min_degree")) c->hubMin = (int)value;
   else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
   else if (!strcmp(name, "record_events")) c->recordEvents = value != 0;
+  else if (!strcmp(name, "merge_exact_max_pairs")) c->mergeExactMax = (int)value;
   else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);
   API_END(c)
 }
@@ -692,6 +738,23 @@ int am3d_download_collection(am3d_ctx* c, int slot, double* out /* [42] */) {
   CK(cudaMemcpy(&cnt, c->collCount.p + slot, sizeof(int), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(&st, c->stamp.p + s, sizeof(long long), cudaMemcpyDeviceToHost));
   out[38] = fl; out[39] = al; out[40] = cnt; out[41] = (double)st;
+  API_END(c)
+}
+
+__global__ void k_list_order(int nb, const int* __restrict__ parent, const long long* __restrict__ stamp, long long* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  int p = parent[i];
+  out[i] = stamp[p >= 0 ? p : i];
+}
+int am3d_download_list_order(am3d_ctx* c, int64_t* out) {
+  API_BEGIN(c)
+  if (!c->haveScene || !out) throw AmError(AM3D_EINVAL, "no scene / null buffer");
+  DevBuf<long long> tmp;
+  tmp.ensure(c->NB + 1);
+  LAUNCH(c, k_list_order, nblk(c->NB), BLK, c->NB, c->parent.p, c->stamp.p, tmp.p);
+  CK(cudaMemcpyAsync(out, tmp.p, c->NB * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   API_END(c)
 }
 

@@ -6,6 +6,7 @@
 // RigidCollection slots, so that the PGS kernels address a merged collection exactly like a free body.
 #pragma once
 #include <chrono>
+#include <future>
 #include <cstdio>
 #include <cstdlib>
 #define DVS 8  // deltaV stride in doubles: 6 used, padded so that a body is two aligned 32-byte accesses
@@ -31,6 +32,7 @@ struct AmError {
 
 // stream of the context whose API call is running on this thread (set by API_BEGIN)
 inline cudaStream_t& amCurrentStream() { static thread_local cudaStream_t s = nullptr; return s; }
+inline cudaMemPool_t& amCurrentPool() { static thread_local cudaMemPool_t p = nullptr; return p; }  // the context's private pool
 inline size_t& amAllocatedBytes() { static size_t b = 0; return b; }  // device bytes handed out by DevBuf (all contexts)
 
 template <class T>
@@ -48,7 +50,7 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
   // Growth goes through the stream-ordered allocator on the calling context's stream: cudaFree / cudaMalloc in the
   // middle of a run cost 10-200 ms each on B200 (measured), cudaMallocAsync / cudaFreeAsync from the retained pool
-  // (release threshold = max, set in am3d_create) cost microseconds and need no device-wide synchronisation.
+  // (a private pool per context with release threshold = max, created in am3d_create) cost microseconds and need no device-wide synchronisation.
   void ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
     if (n <= cap) return;
     size_t ncap = n + n / 2 + 256;  // grow geometrically
@@ -56,7 +58,8 @@ struct DevBuf {
     T* q = nullptr;
     static const bool traceAlloc = getenv("AM3D_TRACE_ALLOC") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
-    CK(cudaMallocAsync(&q, ncap * sizeof(T), s));
+    if (amCurrentPool()) CK(cudaMallocFromPoolAsync(&q, ncap * sizeof(T), amCurrentPool(), s));
+    else CK(cudaMallocAsync(&q, ncap * sizeof(T), s));
     if (keep && p && cap) CK(cudaMemcpyAsync(q, p, cap * sizeof(T), cudaMemcpyDeviceToDevice, s));
     if (p) CK(cudaFreeAsync(p, s));  // ordered after everything already queued on the stream that uses p
     if (traceAlloc)
@@ -131,7 +134,10 @@ struct BpcSet {
 struct am3d_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;  // private stream-ordered allocation pool (nothing of the process's default pool is reconfigured)
   std::string lastError;
+  std::future<int> pending;  // steps handed to the worker thread by am3d_step_async
+  int asyncStatus = 0;
   am3d_params P;
   bool haveScene = false;
   int totalSteps = 0;
@@ -157,6 +163,7 @@ struct am3d_ctx {
   DevBuf<double> x, R, v, w, force, torque, dv, minv, mass, jinv, jinv0, mA, mA0, fric, rest, bbB;
   DevBuf<int> bbCount, flags, scene, parent, btype, collAlive;
   int nCollections = 0;
+  int nMergedLeaves = 0;  // leaves that currently belong to a collection
   long long nextStamp = 0;
   DevBuf<long long> stamp;
   DevBuf<double> metricHist;  // [10] ring (ordered oldest..newest)
@@ -213,7 +220,16 @@ struct am3d_ctx {
   DevBuf<unsigned int> memKey, memKeySorted;
   DevBuf<int> uf, mflag, compEnt, needNew, newScan, target, collCuts, collNComp, collKeeps, leavesFlag, leavesScan, freedFlag;
   DevBuf<unsigned long long> compBest;
-  DevBuf<int> swB1, swB2, swCount, swStart, tmpI2, tmpI3;
+  DevBuf<int> msPar, msSize, msIdent, msSurvivor, msVal, msValSorted, msHead, msScan, msSeg;  // sequential replay of Merging.merge
+  DevBuf<unsigned int> msKey, msKeySorted;
+  DevBuf<int> msList, msList2;
+  DevBuf<unsigned long long> msLKey, msLKey2;
+  int mergeExactMax = 16384;  // mergeable pairs per component up to which the reference's visiting sequence is replayed
+  DevBuf<int> swB1, swB2, swCount, swStart, swAsleep, tmpI2, tmpI3;
+  DevBuf<int> grpLayer, bodyLevel, bfsRound;  // breadth-first layers of the single sweep (getOrganizedContacts)
+  DevBuf<int> phaseHead, phaseScan, sgPhase;  // (layer, colour) phases of the sorted group list
+  int bfsBlocks = 0;
+  bool orderingTimed = false;
   std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples
   bool recordEvents = true; // am3d_set_option("record_events", 0): long batched runs (one device->host copy per merge step saved)
   bool recordOrders = false;
@@ -234,7 +250,7 @@ struct am3d_ctx {
   DevBuf<double> hubDelta;                          // [12] per group
   DevBuf<int> grpDegree, grpHubMask, hubN, hubScan, hubSlot, hubSlotSorted, hubHead, hubRunStart, hubRunBody, hubRunColor, dColorRunStart;
   DevBuf<unsigned long long> hubKey, hubKeySorted;
-  std::vector<int> colorRunStart, colorDense;       // host: first hub run of each (dense) colour; raw colour -> dense index
+  std::vector<int> colorRunStart;                   // host: first hub run of each phase
   int nHubRuns = 0, nHubEntries = 0;
   int hubMin = 64;                                  // degree (in body pairs) from which a body is treated as a hub; 0 = never
   DevBuf<int> scSrc;                                // solve-order -> canonical contact index
@@ -246,7 +262,7 @@ struct am3d_ctx {
 
   // ---- timing --------------------------------------------------------------------------------------
   am3d_timings T;
-  cudaEvent_t ev[20];
+  cudaEvent_t ev[24];
   cudaStream_t copyStream = nullptr;  // device -> host copies of the body state run beside the next step
   cudaEvent_t evSnap = nullptr, evCopied = nullptr;
   bool copyPending = false;

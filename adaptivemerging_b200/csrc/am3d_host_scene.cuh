@@ -43,7 +43,9 @@ static void validateScene(const am3d_scene* s) {
 // (re)initialise every device array from the host copy of the scene: RigidBodySystem.reset() :390-426
 static void resetState(am3d_ctx* c) {
   auto& H = c->H;
-  int NB = H.nb, NC = NB / 2 + 1, NS = NB + NC;
+  // collection slots: at most NB/2 collections are alive, and an unmerge can found up to NB/4 new ones before the
+  // ones it dissolves are retired
+  int NB = H.nb, NC = NB - NB / 4 + 2, NS = NB + NC;
   c->NB = NB; c->NS = NS; c->NSH = H.nsh; c->NN = H.nn; c->NSP = H.nsp;
   // body arrays padded to NS
   auto padD = [&](const std::vector<double>& v, int w) { std::vector<double> r(v); r.resize((size_t)NS * w, 0.0); return r; };
@@ -188,6 +190,7 @@ static void resetState(am3d_ctx* c) {
   c->totalSteps = 0;
   c->mergingEvent = false;
   c->nCollections = 0;
+  c->nMergedLeaves = 0;
   c->nextStamp = NS;
   memset(&c->T, 0, sizeof(c->T));
   CK(cudaStreamSynchronize(c->stream));

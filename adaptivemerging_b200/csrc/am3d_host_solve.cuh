@@ -15,7 +15,9 @@ static ContactPtrs contactPtrs(ContactSet& S) {
 }
 
 // colour the groups (body pairs) so that no two groups of a colour share a non-pinned solver body
-static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, int inCollection) {
+// and order them by (layer, colour) phases; layer = nullptr for the full solve
+static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, int inCollection, const int* layer,
+                         int layerBits) {
   c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
   c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
   c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
@@ -49,27 +51,23 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
     LAUNCH(c, k_color_next_page, nblk(ng), BLK, ng, page - 1, c->grpColor.p);
   }
   int maxColors = (page + 1) * 64;
-  c->colorHist.ensure(maxColors + 1);
-  CK(cudaMemsetAsync(c->colorHist.p, 0, (maxColors + 1) * sizeof(int), c->stream));
-  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, c->grpKey.p, c->grpVal.p, c->colorHist.p);
-  int endBit = 8 + bitsFor((unsigned long long)maxColors);
+  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, c->grpKey.p, c->grpVal.p);
+  int endBit = 20 + (layer ? layerBits : 0);
+  if (!layer) endBit = 8 + bitsFor((unsigned long long)maxColors);
   cubRun(c, [&](void* t, size_t& b) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
   });
-  std::vector<int> hist(maxColors);
-  CK(cudaMemcpyAsync(hist.data(), c->colorHist.p, maxColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  // phases = runs of equal (layer, colour) in the sorted list
+  c->phaseHead.ensure(ng + 2); c->phaseScan.ensure(ng + 2); c->sgPhase.ensure(ng + 2);
+  LAUNCH(c, k_phase_heads, nblk(ng), BLK, ng, c->grpKeySorted.p, c->phaseHead.p);
+  int nPhases = scanTotal(c, c->phaseHead, c->phaseScan, ng);
+  if (nPhases >= (1 << 18)) throw AmError(AM3D_ECAPACITY, "more than 262143 solve phases");
+  c->dColorStart.ensure(nPhases + 2);
+  LAUNCH(c, k_phase_fill, nblk(ng), BLK, ng, c->phaseHead.p, c->phaseScan.p, c->dColorStart.p, c->sgPhase.p);
+  c->colorStart.resize(nPhases + 1);
+  CK(cudaMemcpyAsync(c->colorStart.data(), c->dColorStart.p, (nPhases + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->colorStart.clear();
-  c->colorDense.assign(maxColors, -1);
-  int acc = 0;
-  for (int k = 0; k < maxColors; k++) {
-    if (hist[k] == 0) continue;
-    c->colorDense[k] = (int)c->colorStart.size();
-    c->colorStart.push_back(acc);
-    acc += hist[k];
-  }
-  c->colorStart.push_back(acc);
-  c->nColors = (int)c->colorStart.size() - 1;
+  c->nColors = nPhases;
   c->nGroups = ng;
 }
 
@@ -97,11 +95,46 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   if (nc == 0 || ng == 0) return;
   const int *gb1, *gb2, *gcount, *gstart;
   c->swB1.ensure(ng + 1); c->swB2.ensure(ng + 1); c->swCount.ensure(ng + 1); c->swStart.ensure(ng + 1);
+  c->swAsleep.ensure(ng + 1);
   LAUNCH(c, k_sweep_groups, nblk(ng), BLK, nExt, nInt, c->cur.b1.p, c->cur.b2.p, c->bp.count.p, c->bp.start.p, c->ibp.b1.p,
          c->icon.b1.p, c->icon.b2.p, c->ibp.count.p, c->ibp.start.p, c->ibp.alive.p, c->parent.p, c->flags.p, c->swB1.p, c->swB2.p,
-         c->swCount.p, c->swStart.p);
+         c->swCount.p, c->swStart.p, c->swAsleep.p);
   gb1 = c->swB1.p; gb2 = c->swB2.p; gcount = c->swCount.p; gstart = c->swStart.p;
-  colourGroups(c, ng, gb1, gb2, gcount, sweep ? 1 : 0);
+  const int* layer = nullptr;
+  int layerBits = 0;
+  if (sweep && c->P.organize_contacts) {
+    // getOrganizedContacts (CollisionProcessor.java:346-441): breadth-first layers from the pairs with new contacts
+    CK(cudaEventRecord(c->ev[20], c->stream));
+    c->grpLayer.ensure(ng + 1); c->bodyLevel.ensure(c->NB + 1); c->bfsRound.ensure(8);
+    CK(cudaMemsetAsync(c->grpLayer.p, 0x7f, ng * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->bodyLevel.p, 0x7f, c->NB * sizeof(int), c->stream));
+    CK(cudaMemsetAsync(c->bfsRound.p, 0, 8 * sizeof(int), c->stream));
+    if (ncExt > 0) LAUNCH(c, k_bfs_seed, nblk(ncExt), BLK, ncExt, c->cur.isNew.p, c->cur.bpc.p, c->grpLayer.p);
+    {
+      int ngv = ng;
+      int *gl = c->grpLayer.p, *bl = c->bodyLevel.p, *rd = c->bfsRound.p;
+      void* args[] = {&ngv, &gb1, &gb2, &gcount, &gl, &bl, &rd};
+      int blocks = std::min(c->bfsBlocks, std::max(1, nblk(ng, 256)));
+      if (c->bfsBlocks <= 0) throw AmError(AM3D_ECUDA, "cooperative launch unsupported");
+      CK(cudaLaunchCooperativeKernel((const void*)k_bfs_layers, dim3(blocks), dim3(256), args, 0, c->stream));
+      c->kernelLaunches++;
+    }
+    LAUNCH(c, k_bfs_finalize, nblk(ng), BLK, ng, nExt, c->swAsleep.p, c->bfsRound.p, c->grpLayer.p, c->swCount.p);
+    CK(cudaEventRecord(c->ev[21], c->stream));
+    c->orderingTimed = true;
+    int deepest = readInt(c, c->bfsRound.p + 3);
+    layer = c->grpLayer.p;
+    layerBits = bitsFor((unsigned long long)deepest + 2);
+    if (layerBits > 44) throw AmError(AM3D_ECAPACITY, "too many sweep layers");
+  } else if (sweep) {
+    // organize_contacts = false (CollisionProcessor.java:249-258): external contacts, then the internal contacts of
+    // the awake collections
+    c->grpLayer.ensure(ng + 1);
+    LAUNCH(c, k_plain_layers, nblk(ng), BLK, ng, nExt, c->swAsleep.p, c->grpLayer.p, c->swCount.p);
+    layer = c->grpLayer.p;
+    layerBits = 1;
+  }
+  colourGroups(c, ng, gb1, gb2, gcount, sweep ? 1 : 0, layer, layerBits);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
   c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1);
   c->scP.ensure(24 * (size_t)nc + 48); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1); c->hubDelta.ensure(12 * (size_t)ng + 12);
@@ -120,7 +153,8 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     c->nHubEntries = ne;
     c->hubKey.ensure(ne + 2); c->hubKeySorted.ensure(ne + 2); c->hubSlot.ensure(ne + 2); c->hubSlotSorted.ensure(ne + 2);
     c->hubHead.ensure(ne + 2); c->hubRunStart.ensure(ne + 2); c->hubRunBody.ensure(ne + 2); c->hubRunColor.ensure(ne + 2);
-    LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgBpc.p, c->grpColor.p, c->hubScan.p,
+    if (ng >= (1 << 23) || c->NS >= (1 << 23)) throw AmError(AM3D_ECAPACITY, "hub runs support up to 8M groups / solver bodies");
+    LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgPhase.p, c->hubScan.p,
            c->hubKey.p, c->hubSlot.p);
     cubRun(c, [&](void* t, size_t& b) {
       return cub::DeviceRadixSort::SortPairs(t, b, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, 64, c->stream);
@@ -135,7 +169,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     CK(cudaMemcpyAsync(rc.data(), c->hubRunColor.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     std::vector<int> perColor(c->nColors, 0);
-    for (int r = 0; r < nr; r++) perColor[c->colorDense[rc[r]]]++;
+    for (int r = 0; r < nr; r++) perColor[rc[r]]++;
     for (int k = 0; k < c->nColors; k++) c->colorRunStart[k + 1] = c->colorRunStart[k] + perColor[k];
     c->hubDelta.ensure(12 * (size_t)ng + 12);
     S = solveArrays(c);
@@ -160,8 +194,6 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   long long avgGroups = ng / std::max(1, c->nColors);
   bool persistent = c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
   if (persistent) {
-    c->dColorStart.ensure(c->colorStart.size() + 1);
-    CK(cudaMemcpyAsync(c->dColorStart.p, c->colorStart.data(), c->colorStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     int nColors = c->nColors, chk = sweep ? 0 : 1;
     const int* dcs = c->dColorStart.p;
     const int* dcr = nullptr;
@@ -235,7 +267,7 @@ static void rebuildMembers(am3d_ctx* c) {
   cubRun(c, [&](void* t, size_t& b) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->memKey.p, c->memKeySorted.p, c->memVal.p, c->members.p, nb, 0, bitsFor((unsigned long long)nc + 1), c->stream);
   });
-  scanTotal(c, c->collCount, c->collStart, nc);
+  c->nMergedLeaves = scanTotal(c, c->collCount, c->collStart, nc);
 }
 static int countAlive(am3d_ctx* c) {
   int nc = c->NS - c->NB;
@@ -299,19 +331,45 @@ static void mergeStep(am3d_ctx* c) {
   CK(cudaMemsetAsync(c->compEnt.p, 0, ns * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->compBest.p, 0, ns * sizeof(unsigned long long), c->stream));
   LAUNCH(c, k_merge_census, nblk(ns), BLK, ns, nb, c->collAlive.p, c->parent.p, c->uf.p, c->collCount.p, c->stamp.p, c->compEnt.p, c->compBest.p);
-  LAUNCH(c, k_merge_neednew, nblk(ns), BLK, ns, c->uf.p, c->compEnt.p, c->compBest.p, c->needNew.p);
+  {  // replay the reference's visiting sequence per component to find the surviving collection (k_mseq_run)
+    c->msPar.ensure(ns + 2); c->msSize.ensure(ns + 2); c->msIdent.ensure(ns + 2); c->msSurvivor.ensure(ns + 2);
+    c->msKey.ensure(nFlagged + 2); c->msKeySorted.ensure(nFlagged + 2); c->msVal.ensure(nFlagged + 2); c->msValSorted.ensure(nFlagged + 2);
+    c->msHead.ensure(nFlagged + 2); c->msScan.ensure(nFlagged + 2); c->msSeg.ensure(nFlagged + 2);
+    c->tmpI0.ensure(nbp + 2);
+    LAUNCH(c, k_mseq_init, nblk(ns), BLK, ns, nb, c->collAlive.p, c->collCount.p, c->msPar.p, c->msSize.p, c->msIdent.p, c->msSurvivor.p);
+    c->msList.ensure(nFlagged + 2); c->msLKey.ensure(nFlagged + 2);
+    scanTotal(c, c->mflag, c->tmpI0, nbp);
+    LAUNCH(c, k_mseq_list, nblk(nbp), BLK, nbp, c->mflag.p, c->tmpI0.p, c->bp.key.p, c->msList.p, c->msLKey.p);
+    if (c->bpTail) {  // pairs an unmerge handed back this step sit at the end of the table: restore ascending (lo, hi)
+      c->msList2.ensure(nFlagged + 2); c->msLKey2.ensure(nFlagged + 2);
+      cubRun(c, [&](void* t, size_t& b) {
+        return cub::DeviceRadixSort::SortPairs(t, b, c->msLKey.p, c->msLKey2.p, c->msList.p, c->msList2.p, nFlagged, 0, 48, c->stream);
+      });
+      std::swap(c->msList, c->msList2);
+    }
+    LAUNCH(c, k_mseq_keys, nblk(nFlagged), BLK, nFlagged, c->msList.p, c->bp.b1.p, c->parent.p, c->uf.p, c->msKey.p, c->msVal.p);
+    cubRun(c, [&](void* t, size_t& b) {
+      return cub::DeviceRadixSort::SortPairs(t, b, c->msKey.p, c->msKeySorted.p, c->msVal.p, c->msValSorted.p, nFlagged, 0, bitsFor((unsigned long long)ns), c->stream);
+    });
+    LAUNCH(c, k_seg_heads, nblk(nFlagged), BLK, nFlagged, c->msKeySorted.p, c->msHead.p);
+    int nseg = scanTotal(c, c->msHead, c->msScan, nFlagged);
+    LAUNCH(c, k_seg_fill, nblk(nFlagged), BLK, nFlagged, c->msHead.p, c->msScan.p, c->msSeg.p);
+    LAUNCH(c, k_mseq_run, nblk(nseg, 64), 64, nseg, c->msSeg.p, c->msKeySorted.p, c->msValSorted.p, c->msList.p, c->bp.b1.p, c->bp.b2.p, c->parent.p,
+           c->mergeExactMax, c->msPar.p, c->msSize.p, c->msIdent.p, c->msSurvivor.p);
+  }
+  LAUNCH(c, k_merge_neednew, nblk(ns), BLK, ns, c->uf.p, c->compEnt.p, c->compBest.p, c->msSurvivor.p, c->needNew.p);
   int nNew = scanTotal(c, c->needNew, c->newScan, ns);
   int nfree = freeSlotList(c);
   if (nNew > nfree) throw AmError(AM3D_ECAPACITY, "out of collection slots");
   LAUNCH(c, k_merge_target, nblk(ns), BLK, ns, nb, c->uf.p, c->compEnt.p, c->compBest.p, c->needNew.p, c->newScan.p, c->freeList.p,
-         c->stamp.p, c->collAlive.p, c->target.p);
+         c->stamp.p, c->collAlive.p, c->msSurvivor.p, c->target.p);
   LAUNCH(c, k_merge_target2, nblk(nc), BLK, nc, nb, c->collAlive.p, c->uf.p, c->collCount.p, c->stamp.p, c->compBest.p, c->target.p);
   CK(cudaMemsetAsync(c->collFlagAcc.p, 0, nc * sizeof(int), c->stream));
-  LAUNCH(c, k_merge_newcolls, nblk(ns), BLK, ns, nb, c->uf.p, c->compEnt.p, c->target.p, c->needNew.p, c->newScan.p, c->collAlive.p,
-         c->flags.p, c->stamp.p, c->nextStamp, c->collMode.p, c->metricCount.p);
+  LAUNCH(c, k_merge_newcolls, nblk(ns), BLK, ns, nb, c->uf.p, c->compEnt.p, c->target.p, c->needNew.p, c->newScan.p, c->msSurvivor.p, nFlagged,
+         c->collAlive.p, c->flags.p, c->stamp.p, c->nextStamp, c->collMode.p, c->metricCount.p);
   LAUNCH(c, k_merge_apply, nblk(ns), BLK, ns, nb, c->collAlive.p, c->parent.p, c->uf.p, c->compEnt.p, c->target.p, c->needNew.p,
          c->newScan.p, c->flags.p, c->stamp.p, c->nextStamp, c->collMode.p, c->collFlagAcc.p, c->metricCount.p);
-  c->nextStamp += nNew;
+  c->nextStamp += (long long)nFlagged + nNew;
   recomputeChanged(c);
   // every live external pair whose two bodies now share a collection becomes internal
   c->tmpI0.ensure(nbp + 2); c->tmpI1.ensure(nbp + 2); c->tmpI2.ensure(nbp + 2); c->tmpI3.ensure(nbp + 2);

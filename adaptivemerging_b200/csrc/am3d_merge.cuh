@@ -116,12 +116,105 @@ __global__ void k_merge_census(int ns, int nb, const int* __restrict__ collAlive
     atomicMax(compBest + r, key);
   }
 }
-// components of >1 entity without a pre-existing collection need a fresh slot
+// ---- Merging.merge as the SEQUENCE the reference runs (Merging.java:73-163) ----------------------------------------
+// Which collection object survives a merge, and where a new one enters RigidBodySystem.bodies, depends on the order
+// in which the mergeable pairs are visited: two free bodies found a collection (appended to the list), a free body
+// joins the collection of its partner, of two collections the one with more bodies absorbs the other (ties: body2's,
+// Merging.java:113-129).  The reference visits a HashSet; the oracle canonicalises that to ascending (lo, hi) pair
+// order, which is the order of the body-pair table.  Components of the merge graph are independent, so one thread
+// replays the pairs of one component in that order on a private union-find (dpar/dsize/dident, indexed by top-level
+// entity); components with more than `maxEdges` mergeable pairs fall back to "largest collection survives, ties to
+// the oldest" (k_merge_census) - at those sizes neither the reference nor the oracle can serve as a comparison.
+#define MS_FREE 0x7fffffff
+#define MS_FALLBACK 0x7ffffffe
+__global__ void k_mseq_init(int ns, int nb, const int* __restrict__ collAlive, const int* __restrict__ collCount,
+                            int* __restrict__ dpar, int* __restrict__ dsize, int* __restrict__ dident, int* __restrict__ survivor) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ns) return;
+  dpar[e] = e;
+  bool coll = e >= nb && collAlive[e - nb];
+  dsize[e] = coll ? collCount[e - nb] : 1;
+  dident[e] = coll ? e - nb : MS_FREE;
+  survivor[e] = MS_FALLBACK;
+}
+// the mergeable pairs, in table order (= ascending (lo, hi) unless an unmerge appended pairs this step: then the host
+// sorts them by pair key first)
+__global__ void k_mseq_list(int nbp, const int* __restrict__ mflag, const int* __restrict__ scan,
+                            const unsigned long long* __restrict__ bkey, int* __restrict__ list, unsigned long long* __restrict__ lkey) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbp || !mflag[b]) return;
+  int o = scan[b];
+  list[o] = b;
+  lkey[o] = bkey[b];
+}
+// per mergeable pair (position k in visiting order): component root as sort key, k as value
+__global__ void k_mseq_keys(int n, const int* __restrict__ list, const int* __restrict__ bb1, const int* __restrict__ parent,
+                            const int* __restrict__ uf, unsigned int* __restrict__ key, int* __restrict__ val) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  int l1 = bb1[list[k]];
+  int e = parent[l1] >= 0 ? parent[l1] : l1;
+  key[k] = (unsigned)uf[e];
+  val[k] = k;
+}
+__global__ void k_seg_heads(int n, const unsigned int* __restrict__ key, int* __restrict__ head) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
+}
+__global__ void k_seg_fill(int n, const int* __restrict__ head, const int* __restrict__ scan, int* __restrict__ segStart) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (head[i]) segStart[scan[i]] = i;
+  if (i == n - 1) segStart[scan[i] + head[i]] = n;
+}
+__device__ __forceinline__ int msFind(int* dpar, int e) {
+  while (true) {
+    int p = dpar[e];
+    if (p == e) return e;
+    int g = dpar[p];
+    dpar[e] = g;
+    e = g;
+  }
+}
+__global__ void k_mseq_run(int nseg, const int* __restrict__ segStart, const unsigned int* __restrict__ keySorted,
+                           const int* __restrict__ valSorted, const int* __restrict__ list, const int* __restrict__ bb1, const int* __restrict__ bb2,
+                           const int* __restrict__ parent, int maxEdges, int* __restrict__ dpar, int* __restrict__ dsize,
+                           int* __restrict__ dident, int* __restrict__ survivor) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  int k0 = segStart[s], k1 = segStart[s + 1];
+  int root = (int)keySorted[k0];
+  if (k1 - k0 > maxEdges) return;  // survivor stays MS_FALLBACK
+  for (int k = k0; k < k1; k++) {
+    int seq = valSorted[k];  // position in the visiting order
+    int b = list[seq];
+    int l1 = bb1[b], l2 = bb2[b];
+    int e1 = parent[l1] >= 0 ? parent[l1] : l1, e2 = parent[l2] >= 0 ? parent[l2] : l2;
+    int r1 = msFind(dpar, e1), r2 = msFind(dpar, e2);
+    if (r1 == r2) continue;  // already together (RigidCollection.addIncompleteContacts made the pair internal)
+    int i1 = dident[r1], i2 = dident[r2];
+    int keep, other, ident, size;
+    if (i1 == MS_FREE && i2 == MS_FREE) { keep = r1; other = r2; ident = -1 - seq; size = 2; }             // :100-110
+    else if (i1 != MS_FREE && i2 != MS_FREE) {                                                                  // :111-129
+      if (dsize[r1] > dsize[r2]) { keep = r1; other = r2; } else { keep = r2; other = r1; }
+      ident = dident[keep]; size = dsize[r1] + dsize[r2];
+    } else if (i1 != MS_FREE) { keep = r1; other = r2; ident = i1; size = dsize[r1] + 1; }                    // :130-141
+    else { keep = r2; other = r1; ident = i2; size = dsize[r2] + 1; }                                           // :142-152
+    dpar[other] = keep;
+    dident[keep] = ident;
+    dsize[keep] = size;
+  }
+  survivor[root] = dident[msFind(dpar, root)];
+}
+// components of >1 entity whose surviving collection is a new one need a fresh slot
 __global__ void k_merge_neednew(int ns, const int* __restrict__ uf, const int* __restrict__ compEnt,
-                                const unsigned long long* __restrict__ compBest, int* __restrict__ needNew) {
+                                const unsigned long long* __restrict__ compBest, const int* __restrict__ survivor,
+                                int* __restrict__ needNew) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= ns) return;
-  needNew[r] = (uf[r] == r && compEnt[r] > 1 && compBest[r] == 0ULL) ? 1 : 0;
+  bool comp = uf[r] == r && compEnt[r] > 1;
+  int sv = survivor[r];
+  needNew[r] = (comp && (sv == MS_FALLBACK ? compBest[r] == 0ULL : sv < 0)) ? 1 : 0;
 }
 __global__ void k_free_slots(int nc, const int* __restrict__ collAlive, int* __restrict__ isFree) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,12 +229,13 @@ __global__ void k_merge_target(int ns, int nb, const int* __restrict__ uf, const
                                const unsigned long long* __restrict__ compBest, const int* __restrict__ needNew,
                                const int* __restrict__ newScan, const int* __restrict__ freeList,
                                const long long* __restrict__ stamp, const int* __restrict__ collAlive,
-                               int* __restrict__ target) {
+                               const int* __restrict__ survivor, int* __restrict__ target) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= ns) return;
   target[r] = -1;
   if (uf[r] != r || compEnt[r] <= 1) return;
   if (needNew[r]) target[r] = freeList[newScan[r]];
+  else if (survivor[r] != MS_FALLBACK) target[r] = survivor[r];
   else {
     // recover the slot from the winning (count, stamp) key: find the collection of this component with that stamp
     target[r] = -2;  // resolved by k_merge_target2
@@ -187,7 +281,8 @@ __global__ void k_merge_apply(int ns, int nb, int* __restrict__ collAlive, int* 
 }
 __global__ void k_merge_newcolls(int ns, int nb, const int* __restrict__ uf, const int* __restrict__ compEnt,
                                  const int* __restrict__ target, const int* __restrict__ needNew,
-                                 const int* __restrict__ newScan, int* __restrict__ collAlive, int* __restrict__ flags,
+                                 const int* __restrict__ newScan, const int* __restrict__ survivor, int nFlagged,
+                                 int* __restrict__ collAlive, int* __restrict__ flags,
                                  long long* __restrict__ stamp, long long stampBase, int* __restrict__ collMode,
                                  int* __restrict__ metricCount) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,7 +293,9 @@ __global__ void k_merge_newcolls(int ns, int nb, const int* __restrict__ uf, con
   if (needNew[r]) {
     collAlive[tg] = 1;
     flags[nb + tg] = 0;
-    stamp[nb + tg] = stampBase + newScan[r];  // appended to RigidBodySystem.bodies in creation order
+    // appended to RigidBodySystem.bodies when the pair that founded it was visited
+    int sv = survivor[r];
+    stamp[nb + tg] = sv == MS_FALLBACK ? stampBase + nFlagged + newScan[r] : stampBase + (-1 - sv);
     metricCount[nb + tg] = 0;
   }
 }
@@ -643,23 +740,91 @@ __global__ void k_sweep_groups(int nExt, int nInt, const int* __restrict__ ecb1,
                                const int* __restrict__ icb1, const int* __restrict__ icb2, const int* __restrict__ icount,
                                const int* __restrict__ istart, const int* __restrict__ ialive, const int* __restrict__ parent,
                                const int* __restrict__ flags, int* __restrict__ gb1, int* __restrict__ gb2,
-                               int* __restrict__ gcount, int* __restrict__ gstart) {
+                               int* __restrict__ gcount, int* __restrict__ gstart, int* __restrict__ gasleep) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nExt + nInt) return;
   // The bodies of a group are taken in the orientation of ITS CONTACTS (Contact.body1/body2 of this step), which can
   // differ from the orientation the BodyPairContact object was created with once list positions changed.
   if (g < nExt) {
     int s = estart[g];
-    gb1[g] = ecb1[s]; gb2[g] = ecb2[s]; gcount[g] = ecount[g]; gstart[g] = s;
+    gb1[g] = ecb1[s]; gb2[g] = ecb2[s]; gcount[g] = ecount[g]; gstart[g] = s; gasleep[g] = 0;
   } else {
+    // internal pair of a collection.  Pairs of a SLEEPING collection take part in the sweep only if the breadth-first
+    // walk from the new contacts reaches them (CollisionProcessor.java:389-394 walks body.bodyPairContacts without
+    // looking at sleeping flags; only the "missing bpc from collections" pass :405-415 skips sleeping collections)
     int b = g - nExt;
     int s = istart[b];
     bool live = ialive[b] && icount[b] > 0;
     int p = live ? parent[ib1[b]] : -1;
-    bool on = live && p >= 0 && !(flags[p] & AM3D_F_SLEEPING);
+    live = live && p >= 0;
     gb1[g] = live ? icb1[s] : 0; gb2[g] = live ? icb2[s] : 0; gstart[g] = s;
-    gcount[g] = on ? icount[b] : 0;
+    gcount[g] = live ? icount[b] : 0;
+    gasleep[g] = (live && (flags[p] & AM3D_F_SLEEPING)) ? 1 : 0;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// getOrganizedContacts (CollisionProcessor.java:346-441): breadth-first layers over the body-pair graph, starting from
+// the pairs that hold a contact that is new this time step; two pairs are neighbours when they share a leaf body
+// (pinned ones included: body.bodyPairContacts of the plane lists every pair resting on it).
+// ------------------------------------------------------------------------------------------------
+#define BFS_INF 0x7f7f7f7f
+__global__ void k_bfs_seed(int nc, const int* __restrict__ isNew, const int* __restrict__ cbpc, int* __restrict__ grpLayer) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  if (isNew[i] && cbpc[i] >= 0) grpLayer[cbpc[i]] = 0;
+}
+// cooperative: one grid barrier per layer.  round[3] = "something was reached" flags, rotating; round[3] = deepest layer
+__global__ void __launch_bounds__(256)
+k_bfs_layers(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ gcount,
+             int* __restrict__ grpLayer, int* __restrict__ bodyLevel, int* __restrict__ round) {
+  cg::grid_group grid = cg::this_grid();
+  int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int g = tid; g < ng; g += stride)
+    if (gcount[g] > 0 && grpLayer[g] == 0) { atomicMin(bodyLevel + gb1[g], 0); atomicMin(bodyLevel + gb2[g], 0); }
+  grid.sync();
+  for (int L = 1;; L++) {
+    if (tid == 0) round[(L + 1) % 3] = 0;
+    bool any = false;
+    for (int g = tid; g < ng; g += stride) {
+      if (gcount[g] > 0 && grpLayer[g] == BFS_INF) {
+        int a = gb1[g], b = gb2[g];
+        if (__ldcg(bodyLevel + a) < L || __ldcg(bodyLevel + b) < L) {
+          grpLayer[g] = L;
+          atomicMin(bodyLevel + a, L);
+          atomicMin(bodyLevel + b, L);
+          any = true;
+        }
+      }
+    }
+    if (any) round[L % 3] = 1;
+    grid.sync();
+    if (__ldcg(round + L % 3) == 0) {
+      if (tid == 0) round[3] = L - 1;
+      break;
+    }
+  }
+}
+// pairs the walk did not reach: external ones follow the last layer, internal ones of awake collections come last,
+// internal ones of sleeping collections stay out of the sweep
+__global__ void k_bfs_finalize(int ng, int nExt, const int* __restrict__ gasleep, const int* __restrict__ round,
+                               int* __restrict__ grpLayer, int* __restrict__ gcount) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  if (grpLayer[g] != BFS_INF) return;
+  int deepest = round[3];
+  if (g < nExt) grpLayer[g] = deepest + 1;
+  else {
+    grpLayer[g] = deepest + 2;
+    if (gasleep[g]) gcount[g] = 0;
+  }
+}
+// organize_contacts = false: external pairs first, then the internal pairs of awake collections
+__global__ void k_plain_layers(int ng, int nExt, const int* __restrict__ gasleep, int* __restrict__ grpLayer, int* __restrict__ gcount) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  grpLayer[g] = g < nExt ? 0 : 1;
+  if (g >= nExt && gasleep[g]) gcount[g] = 0;
 }
 // after the sweep: sub-bodies of awake collections advance their velocities with their own deltaV
 // (CollisionProcessor.java:289-297), then every deltaV is zeroed for the full solve (:299)

@@ -502,7 +502,10 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
     if (parent[a] >= 0) a = parent[a];
     if (parent[b] >= 0) b = parent[b];
   }
-  bool pa = flags[a] & AM3D_F_PINNED, pb = flags[b] & AM3D_F_PINNED;
+  int cnt = gcount[g];
+  // groups without contacts in this solve (dead pairs, internal pairs of sleeping collections the sweep does not reach)
+  // constrain nobody
+  bool pa = (flags[a] & AM3D_F_PINNED) || cnt == 0, pb = (flags[b] & AM3D_F_PINNED) || cnt == 0;
   sb1[g] = pa ? -1 - a : a;
   sb2[g] = pb ? -1 - b : b;
   if (!pa) atomicAdd(degree + a, 1);
@@ -510,7 +513,6 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
   // Jones-Plassmann priority: hashed, except that long groups (sphere-tree pairs with hundreds of contacts, solved
   // as one sequential chain) come first by size class: giants that do not touch each other then share the first
   // colours, and a sweep costs the longest chain per colour instead of one giant per colour
-  int cnt = gcount[g];
   unsigned long long cls = cnt > 64 ? (unsigned long long)(32 - __clz(cnt >> 6)) : 0ULL;
   prio[g] = (cls << 59) | ((unsigned long long)(hash32((unsigned)g) >> 5) << 32) | (unsigned)(g + 1);
   color[g] = -1;
@@ -572,16 +574,32 @@ __global__ void k_color_next_page(int ng, int page, int* __restrict__ color) {
   if (g >= ng) return;
   if (color[g] == -2 - page) color[g] = -1;
 }
-// solve order: by colour; inside a colour (any order gives the same result: the groups share no free body) by
-// descending contact count so that the lanes of a warp run the same number of contacts; ties by group index
-// (the radix sort is stable)
-__global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount,
-                                unsigned long long* __restrict__ key, int* __restrict__ val, int* __restrict__ hist) {
+// solve order: by (layer, colour) = one PHASE of the sweep; inside a phase (any order gives the same result: the groups
+// share no free body) by descending contact count so that the lanes of a warp run the same number of contacts; ties by
+// group index (the radix sort is stable).  layer = breadth-first distance from the body pairs that hold new contacts
+// (getOrganizedContacts, CollisionProcessor.java:346-441) for the single sweep, absent (0) for the full solve.
+__global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount, const int* __restrict__ layer,
+                                unsigned long long* __restrict__ key, int* __restrict__ val) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
-  key[g] = ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
+  unsigned long long L = layer ? (unsigned long long)(unsigned)layer[g] : 0ULL;
+  key[g] = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
   val[g] = g;
-  atomicAdd(hist + color[g], 1);
+}
+// phases of the sorted group list: head = first group of a (layer, colour) class
+__global__ void k_phase_heads(int ng, const unsigned long long* __restrict__ key, int* __restrict__ head) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  head[p] = (p == 0 || (key[p] >> 8) != (key[p - 1] >> 8)) ? 1 : 0;
+}
+__global__ void k_phase_fill(int ng, const int* __restrict__ head, const int* __restrict__ scan, int* __restrict__ phaseStart,
+                             int* __restrict__ phaseOf) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  int ph = scan[p] + head[p] - 1;
+  phaseOf[p] = ph;
+  if (head[p]) phaseStart[ph] = p;
+  if (p == ng - 1) phaseStart[ph + 1] = ng;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -989,15 +1007,15 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __r
 // hub entries: one per (group, hub side), keyed (colour, hub body, group position) so that a radix sort groups them
 // into (colour, hub) runs with ascending group position
 __global__ void k_hub_entries(int ng, const int* __restrict__ sgFlags, const int* __restrict__ sgB1, const int* __restrict__ sgB2,
-                              const int* __restrict__ sgBpc, const int* __restrict__ grpColor, const int* __restrict__ scan,
+                              const int* __restrict__ phaseOf, const int* __restrict__ scan,
                               unsigned long long* __restrict__ key, int* __restrict__ slot) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ng) return;
   int fl = sgFlags[p];
   int o = scan[p];
-  unsigned long long col = (unsigned long long)grpColor[sgBpc[p]];
-  if (fl & SG_HUB1) { key[o] = (col << 52) | ((unsigned long long)sgB1[p] << 26) | (unsigned long long)p; slot[o] = 2 * p; o++; }
-  if (fl & SG_HUB2) { key[o] = (col << 52) | ((unsigned long long)sgB2[p] << 26) | (unsigned long long)p; slot[o] = 2 * p + 1; }
+  unsigned long long col = (unsigned long long)phaseOf[p];  // < 2^18 phases, bodies < 2^23, groups < 2^23 (checked on the host)
+  if (fl & SG_HUB1) { key[o] = (col << 46) | ((unsigned long long)sgB1[p] << 23) | (unsigned long long)p; slot[o] = 2 * p; o++; }
+  if (fl & SG_HUB2) { key[o] = (col << 46) | ((unsigned long long)sgB2[p] << 23) | (unsigned long long)p; slot[o] = 2 * p + 1; }
 }
 __global__ void k_hub_sides(int ng, const int* __restrict__ sgFlags, int* __restrict__ n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1008,7 +1026,7 @@ __global__ void k_hub_sides(int ng, const int* __restrict__ sgFlags, int* __rest
 __global__ void k_hub_run_heads(int ne, const unsigned long long* __restrict__ key, int* __restrict__ head) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
-  head[e] = (e == 0 || (key[e] >> 26) != (key[e - 1] >> 26)) ? 1 : 0;
+  head[e] = (e == 0 || (key[e] >> 23) != (key[e - 1] >> 23)) ? 1 : 0;
 }
 __global__ void k_hub_run_fill(int ne, const unsigned long long* __restrict__ key, const int* __restrict__ head,
                                const int* __restrict__ scan, int* __restrict__ runStart, int* __restrict__ runBody,
@@ -1017,8 +1035,8 @@ __global__ void k_hub_run_fill(int ne, const unsigned long long* __restrict__ ke
   if (e >= ne || !head[e]) return;
   int r = scan[e];
   runStart[r] = e;
-  runBody[r] = (int)((key[e] >> 26) & 0x3ffffff);
-  runColor[r] = (int)(key[e] >> 52);
+  runBody[r] = (int)((key[e] >> 23) & 0x7fffff);
+  runColor[r] = (int)(key[e] >> 46);
 }
 
 __global__ void k_iter_end(unsigned long long* iterState, double tolerance, int checkTolerance) {

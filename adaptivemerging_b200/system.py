@@ -89,6 +89,15 @@ class RigidBodySystem:
         self.unmergingTime = t.unmerging
         self.warmStartTime = t.warmstart
 
+    def step_async(self, dt, nsteps=1):
+        """hand nsteps to the context's worker thread and return (am3d_step_async); sync() waits"""
+        self._ck(self._L.am3d_step_async(self._h, float(dt), int(nsteps)))
+        self.totalSteps += nsteps
+        self.simulationTime += dt * nsteps
+
+    def sync(self):
+        self._ck(self._L.am3d_sync(self._h))
+
     def reset(self):
         self._ck(self._L.am3d_reset(self._h))
         self.simulationTime = 0.0
@@ -215,6 +224,12 @@ class RigidBodySystem:
         self._ck(self._L.am3d_download_collection(self._h, int(slot), _p(out)))
         return dict(x=out[0:3], R=out[3:12], v=out[12:15], omega=out[15:18], mass=out[18], minv=out[19], jinv=out[20:29],
                     mA=out[29:38], flags=int(out[38]), alive=int(out[39]), count=int(out[40]), stamp=int(out[41]))
+
+    def list_order(self):
+        """rank of every leaf body's top-level entity in RigidBodySystem.bodies (0 = first in the list)"""
+        out = np.zeros(self.n_bodies, np.int64)
+        self._ck(self._L.am3d_download_list_order(self._h, _p(out)))
+        return np.unique(out, return_inverse=True)[1]
 
     def set_option(self, name, value):
         self._ck(self._L.am3d_set_option(self._h, name.encode(), float(value)))

@@ -33,8 +33,10 @@ extern "C" {
 #define AM3D_ECUDA (-2)        /* CUDA runtime error (message in last_error)   */
 #define AM3D_ENOGPU (-3)       /* no usable device: there is NO CPU fallback   */
 #define AM3D_EUNSUPPORTED (-4) /* option of the reference not built yet        */
-#define AM3D_ECAPACITY (-5)    /* a device buffer overflowed; it was regrown,  \
-                                  re-run the step from the previous state     */
+#define AM3D_ECAPACITY (-5)    /* a hard capacity limit was hit in the middle  \
+                                  of a step (collection slots, colours, tree   \
+                                  stack): the step is NOT rolled back, call    \
+                                  am3d_reset before stepping again             */
 #define AM3D_ESTATE (-6)       /* call order (e.g. step before upload_scene)   */
 
 /* body types: XMLParser.parseBody (XMLParser.java:151-163) */
@@ -270,7 +272,9 @@ int am3d_reset(am3d_ctx* ctx);
 
 /* replaces RigidBodySystem.advanceTime(dt) (:102-185), nsteps times */
 int am3d_step(am3d_ctx* ctx, double dt, int nsteps);
-/* async variant for batched shards: enqueue and return; am3d_sync waits */
+/* async variant for batched shards driven from one host thread: the steps are handed to the context's own worker
+ * thread (which runs the host side of the step and its kernels) and the call returns at once; am3d_sync waits for
+ * them and returns their status.  Any other call on the same ctx first waits for the pending steps. */
 int am3d_step_async(am3d_ctx* ctx, double dt, int nsteps);
 int am3d_sync(am3d_ctx* ctx);
 
@@ -329,6 +333,9 @@ int am3d_num_internal_bpcs(am3d_ctx* ctx);
 int am3d_download_internal_bpcs(am3d_ctx* ctx, am3d_bpc* out, int capacity, int* count);
 /* one RigidCollection: x[3] R[9] v[3] omega[3] mass minv jinv[9] massAngular[9] flags alive members stamp */
 int am3d_download_collection(am3d_ctx* ctx, int slot, double* out42);
+/* position of every leaf body's top-level entity (the body itself or its RigidCollection) in RigidBodySystem.bodies,
+ * as a monotone key: sorting by it gives the list order the Java side has to mirror (Merging.java:105-110, :269-270) */
+int am3d_download_list_order(am3d_ctx* ctx, int64_t* out /* [n_bodies] */);
 /* engine options that are not reference parameters: "hub_min_degree" (body pairs per body from which a body is a
  * hub of the contact graph, 0 = never; default 64), "pgs_persistent" (0 never / 1 heuristic / 2 always),
  * "record_events" (merge / unmerge event log for am3d_download_events, default 1; 0 saves a read-back per merge step) */

@@ -1482,13 +1482,15 @@ struct System {
     return false;
   }
   void getNextLayer(std::vector<BPC*> layer, std::vector<BPC*>& ordered) {
+    int depth = 0;
     while (true) {
       std::vector<BPC*> next;
+      depth++;
       for (BPC* bpc : layer) {
         for (int i = 0; i < 2; i++) {
           Body* body = bpc->getBody(i);
           for (BPC* other : body->bodyPairContacts) {
-            if (!other->checked) { next.push_back(other); other->checked = true; }
+            if (!other->checked) { next.push_back(other); other->checked = true; other->layer = depth; }
           }
         }
       }
@@ -1496,27 +1498,32 @@ struct System {
       ordered.insert(ordered.end(), next.begin(), next.end());
       layer = next;
     }
+    lastDepth = depth;
   }
   // getOrganizedContacts :346-419
+  int lastDepth = 0;
   void getOrganizedContacts(std::vector<Contact*>& out) {
     std::vector<BPC*> ordered;
+    lastDepth = 0;
     for (BPC* bpc : bodyPairContacts) {
       for (Contact* c : bpc->contactList) {
-        if (c->newThisTimeStep) { ordered.push_back(bpc); bpc->checked = true; break; }
+        if (c->newThisTimeStep) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = 0; break; }
       }
     }
     // (picked bodies: UI only, never set here)
     if (!ordered.empty()) getNextLayer(ordered, ordered);
     for (BPC* bpc : bodyPairContacts)
-      if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; }
+      if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 1; }
     for (Body* body : bodies) {
       if (body->isCollection && !body->sleeping) {
         for (BPC* bpc : body->bodyPairContacts)
-          if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; }
+          if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 2; }
       }
     }
-    for (BPC* bpc : ordered) out.insert(out.end(), bpc->contactList.begin(), bpc->contactList.end());
+    for (BPC* bpc : ordered)
+      for (Contact* c : bpc->contactList) { out.push_back(c); sweepLayerOf[c] = bpc->layer; }
   }
+  std::map<Contact*, int> sweepLayerOf;  // test bookkeeping: getOrganizedContacts class of every contact of the sweep
   static void updateJacobiansThatNeedUpdating(std::vector<Contact*>& list, bool computeInCollection) {
     for (Contact* c : list)
       if (c->body1->parent != nullptr || c->body2->parent != nullptr) computeJacobian(c, computeInCollection);
@@ -1572,18 +1579,30 @@ struct System {
     double t0 = nowSec();
     if (!hasCollections()) return;
     std::vector<Contact*> list;
+    sweepLayerOf.clear();
     if (P.organize_contacts) {
       double t1 = nowSec();
       getOrganizedContacts(list);
       T.contact_ordering = nowSec() - t1;
     } else {
       list = contacts;
+      for (Contact* c : list) sweepLayerOf[c] = 0;
       for (Body* body : bodies)
         if (body->isCollection && !body->sleeping)
-          list.insert(list.end(), body->internalContacts.begin(), body->internalContacts.end());
+          for (Contact* c : body->internalContacts) { list.push_back(c); sweepLayerOf[c] = 1; }
     }
     std::vector<OrderMeta> meta;
     bool hubs = haveOrderSweep && applyOrder(list, orderSweep, meta);
+    if (haveOrderSweep) {
+      // the replayed sequence may permute contacts only INSIDE a class of the reference's order (new-contact pairs,
+      // each breadth-first layer, the unconnected rest): classes must appear in the reference's sequence
+      int prev = -1;
+      for (Contact* c : list) {
+        int L = sweepLayerOf[c];
+        if (L < prev) orderMismatch++;
+        prev = std::max(prev, L);
+      }
+    }
     updateJacobiansThatNeedUpdating(list, true);
     double t2 = nowSec();
     if (hubs) pgsSolveHub(list, meta, dt, P.iterations_in_collection, 1e-5, 1., P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., true);
@@ -1936,6 +1955,17 @@ void amo_get_bodies(void* h, double* x, double* R, double* v, double* omega, int
     if (omega) { omega[3 * i] = b->omega.x; omega[3 * i + 1] = b->omega.y; omega[3 * i + 2] = b->omega.z; }
     if (sleeping) sleeping[i] = (b->parent ? b->parent->sleeping : b->sleeping) ? 1 : 0;
     if (collection) collection[i] = b->parent ? b->parent->collectionSlot : -1;
+  }
+}
+// rank of every leaf body's top-level entity in `bodies` (list order)
+void amo_get_list_order(void* h, int32_t* out) {
+  System* s = (System*)h;
+  std::map<const amo::Body*, int> pos;
+  for (size_t k = 0; k < s->bodies.size(); k++) pos[s->bodies[k]] = (int)k;
+  for (size_t i = 0; i < s->leaf.size(); i++) {
+    const amo::Body* b = s->leaf[i].get();
+    auto it = pos.find(b->parent ? b->parent : b);
+    out[i] = it == pos.end() ? -1 : it->second;
   }
 }
 // teacher forcing: overwrite the state of every leaf body (no collections may exist)

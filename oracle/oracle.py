@@ -31,7 +31,7 @@ def lib():
         L.amo_create.argtypes = [C.c_void_p, C.c_void_p]
         for name in ["amo_destroy", "amo_set_params", "amo_get_bodies", "amo_set_bodies", "amo_get_timings",
                      "amo_apply_external_forces", "amo_set_lambdas", "amo_get_deltav", "amo_set_next_orders",
-                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals"]:
+                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order"]:
             getattr(L, name).restype = None
         for name in ["amo_row_updates", "amo_solve_seconds"]:
             getattr(L, name).restype = C.c_double
@@ -141,6 +141,11 @@ class Oracle:
         v = np.ascontiguousarray(dv, np.float64) if dv is not None else None
         w = np.ascontiguousarray(domega, np.float64) if domega is not None else None
         self.L.amo_add_body_velocity(self.h, body, _p(v), _p(w))
+
+    def list_order(self):
+        out = np.zeros(self.n, np.int32)
+        self.L.amo_get_list_order(self.h, _p(out))
+        return out
 
     def residuals(self):
         out = np.zeros(4)

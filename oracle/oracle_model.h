@@ -137,6 +137,7 @@ struct BPC {
   std::vector<ContactState> contactStateHist;
   bool inCollection = false;
   bool checked = false;
+  int layer = 0;  // position class in getOrganizedContacts (test bookkeeping: 0 = holds a new contact, k = k-th BFS layer, ...)
   BPC(Body* a, Body* b) : body1(a), body2(b) {}
   Body* getBody(int i) const { return i == 0 ? body1 : body2; }
   Body* getOtherBody(const Body* b) const { return body1 == b ? body2 : (body2 == b ? body1 : nullptr); }

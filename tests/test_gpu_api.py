@@ -59,3 +59,27 @@ def test_reset_repeats_the_run_bit_for_bit():
     assert np.array_equal(first["collection"], second["collection"])
     assert ev1 == ev2 and len(ev1) > 0
     s.close()
+
+
+def test_step_async_returns_before_the_steps_are_done():
+    """am3d_step_async hands the steps to the context's worker thread: the call returns at once, am3d_sync waits, and the
+    result is the one am3d_step gives; two contexts driven from one host thread overlap."""
+    import time
+    blob = golden_scene("tower25platform")
+    p = apply_overrides(default_params(), blob.overrides)
+    a = RigidBodySystem(0).load(blob, p)
+    b = RigidBodySystem(0).load(blob, p)
+    a.advanceTime(0.05, 5); b.advanceTime(0.05, 5)      # warm both contexts
+    t0 = time.perf_counter(); a.advanceTime(0.05, 150); t_sync = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    b.step_async(0.05, 150)
+    t_call = time.perf_counter() - t0
+    b.sync()
+    t_total = time.perf_counter() - t0
+    assert t_call < 0.2 * t_sync, (t_call, t_sync)       # returned long before 150 steps could have run
+    assert t_total > 0.5 * t_sync
+    ga, gb = a.bodies(), b.bodies()
+    for k in ("x", "R", "v", "omega"):
+        assert np.array_equal(ga[k].view(np.uint64), gb[k].view(np.uint64)), k
+    assert a.events().tolist() == b.events().tolist()
+    a.close(); b.close()

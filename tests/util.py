@@ -97,9 +97,12 @@ def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
         worst = max(worst, err)
         gpu.max_contacts = max(getattr(gpu, "max_contacts", 0), gpu.timings().n_contacts)
         assert gpu.timings().n_contacts == cpu.timings().n_contacts, f"step {step}: contact counts differ"
+        assert gpu.timings().n_bodies == cpu.timings().n_bodies, f"step {step}: bodies.size() differs"  # CSV column 1
         assert err < tol, f"step {step}: state error {err:.3e}"
         assert np.array_equal(g["sleeping"], o["sleeping"]), f"step {step}: sleeping flags differ"
         assert np.array_equal(g["collection"] >= 0, o["collection"] >= 0), f"step {step}: merged sets differ"
+        # RigidBodySystem.bodies list order (decides Contact.body1/body2 and the emission order of later steps)
+        assert np.array_equal(gpu.list_order(), np.unique(cpu.list_order(), return_inverse=True)[1]), f"step {step}: body list order differs"
     ev_g = sorted(map(tuple, gpu.events().tolist()))
     ev_o = sorted(map(tuple, cpu.events().tolist()))
     return gpu, cpu, ev_g, ev_o, worst
