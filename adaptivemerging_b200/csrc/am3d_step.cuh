@@ -492,7 +492,7 @@ __device__ __forceinline__ unsigned int hash32(unsigned int a) {
 }
 // solver bodies of a group: parent collection unless computeInCollection; negative (-1 - body) for a pinned body
 __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ parent,
-                           const int* __restrict__ flags, const int* __restrict__ gcount, int inCollection,
+                           const int* __restrict__ flags, const int* __restrict__ gcount, const int* __restrict__ bodyLocal, int inCollection,
                            int* __restrict__ sb1, int* __restrict__ sb2, unsigned long long* __restrict__ prio,
                            int* __restrict__ color, int* __restrict__ degree) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -514,7 +514,12 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
   // as one sequential chain) come first by size class: giants that do not touch each other then share the first
   // colours, and a sweep costs the longest chain per colour instead of one giant per colour
   unsigned long long cls = cnt > 64 ? (unsigned long long)(32 - __clz(cnt >> 6)) : 0ULL;
-  prio[g] = (cls << 59) | ((unsigned long long)(hash32((unsigned)g) >> 5) << 32) | (unsigned)(g + 1);
+  // the hash is taken over the SCENE-LOCAL ids of the two leaf bodies and ties go to the lower group index, whose
+  // order inside a scene does not depend on the other scenes of the context: a scene is coloured (and therefore
+  // solved) the same way alone and as one of many batched copies
+  unsigned la = (unsigned)bodyLocal[gb1[g]], lb = (unsigned)bodyLocal[gb2[g]];
+  unsigned h = hash32(hash32(la) * 0x9E3779B1u + lb);
+  prio[g] = (cls << 59) | ((unsigned long long)(h >> 5) << 32) | (unsigned)(g + 1);
   color[g] = -1;
 }
 // Hubs: non-pinned solver bodies touched by >= hubMin groups (a funnel, a big merged collection).  A hub side takes
@@ -578,13 +583,27 @@ __global__ void k_color_next_page(int ng, int page, int* __restrict__ color) {
 // share no free body) by descending contact count so that the lanes of a warp run the same number of contacts; ties by
 // group index (the radix sort is stable).  layer = breadth-first distance from the body pairs that hold new contacts
 // (getOrganizedContacts, CollisionProcessor.java:346-441) for the single sweep, absent (0) for the full solve.
+// With sceneShift > 0 (batched scenes solved one CTA per scene) the scene id leads the key, so that every scene's
+// phases are contiguous.
 __global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount, const int* __restrict__ layer,
+                                const int* __restrict__ gb1, const int* __restrict__ bodyScene, int sceneShift,
                                 unsigned long long* __restrict__ key, int* __restrict__ val) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   unsigned long long L = layer ? (unsigned long long)(unsigned)layer[g] : 0ULL;
-  key[g] = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
+  unsigned long long k = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
+  if (sceneShift > 0) k |= (unsigned long long)(unsigned)bodyScene[gb1[g]] << sceneShift;
+  key[g] = k;
   val[g] = g;
+}
+// per scene: its range of phases (scenes without groups keep start = end = 0)
+__global__ void k_scene_phases(int nPhases, const int* __restrict__ phaseStart, const unsigned long long* __restrict__ key,
+                               int sceneShift, int* __restrict__ sceneRange /* [2 * nScenes] */) {
+  int ph = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ph >= nPhases) return;
+  int s = (int)(key[phaseStart[ph]] >> sceneShift);
+  if (ph == 0 || (int)(key[phaseStart[ph - 1]] >> sceneShift) != s) sceneRange[2 * s] = ph;
+  if (ph == nPhases - 1 || (int)(key[phaseStart[ph + 1]] >> sceneShift) != s) sceneRange[2 * s + 1] = ph + 1;
 }
 // phases of the sorted group list: head = first group of a (layer, colour) class
 __global__ void k_phase_heads(int ng, const unsigned long long* __restrict__ key, int* __restrict__ head) {
@@ -607,6 +626,7 @@ __global__ void k_phase_fill(int ng, const int* __restrict__ head, const int* __
 // ------------------------------------------------------------------------------------------------
 struct SolveArrays {
   int *sgB1, *sgB2, *sgStart, *sgCount, *sgFlags, *sgBpc;
+  int *sgL1, *sgL2;  // scene-local deltaV slots of the two solver bodies (per-scene solve), -1 = pinned
   double *sgMass, *sgMu;
   double* scP;       // [24] per contact, solve order: n t1 t2 (9) | r1 r2 (6) | b (3) | D (3) | lambda (3)
   int *scSrc, *scState;
@@ -622,7 +642,8 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
                               const int* __restrict__ gcount, const double* __restrict__ minv,
                               const double* __restrict__ jinv, const double* __restrict__ fric,
                               const int* __restrict__ flags, const int* __restrict__ hubMask, int frictionOverride,
-                              double frictionVal, SolveArrays S, int* __restrict__ grpPos) {
+                              double frictionVal, const int* __restrict__ bodyLocal, const int* __restrict__ collRep, int nb,
+                              SolveArrays S, int* __restrict__ grpPos) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ng) return;
   int g = order[p];
@@ -631,6 +652,10 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
   int ia = a >= 0 ? a : -1 - a, ib = b >= 0 ? b : -1 - b;
   S.sgB1[p] = a >= 0 ? a : -1;
   S.sgB2[p] = b >= 0 ? b : -1;
+  // deltaV slot inside the scene: a leaf uses its scene-local id, a collection the id of its first member (which,
+  // being merged, is no solver body of this solve itself)
+  S.sgL1[p] = a >= 0 ? bodyLocal[a < nb ? a : collRep[a - nb]] : -1;
+  S.sgL2[p] = b >= 0 ? bodyLocal[b < nb ? b : collRep[b - nb]] : -1;
   S.sgCount[p] = gcount[g];
   S.sgBpc[p] = g;
   double* M = S.sgMass + 20 * p;
@@ -779,10 +804,11 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
 // A hub side works on a private copy of the hub's deltaV as of the start of the colour (plus this group's own
 // updates) and hands what it added to hubDelta; k_hub_reduce folds the deltas in after the colour, in a fixed order.
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-template <int MODE, bool HUB>
+// SM = true: dv is the CTA's shared-memory deltaV table of one scene (6 doubles per scene-local slot).
+template <int MODE, bool HUB, bool SM = false>
 __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
                                          double& localMax) {
-  int a = S.sgB1[p], b = S.sgB2[p];
+  int a = SM ? S.sgL1[p] : S.sgB1[p], b = SM ? S.sgL2[p] : S.sgB2[p];
   int start = S.sgStart[p], cnt = S.sgCount[p];
   const double* PK0 = S.scP + 24 * (size_t)start;
   if (cnt > 0) { prefetchL2(PK0); prefetchL2(PK0 + 16); }
@@ -797,8 +823,13 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
   for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
-  if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
-  if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
+  if (SM) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { if (a >= 0) dv1[k] = dv[6 * a + k]; if (b >= 0) dv2[k] = dv[6 * b + k]; }
+  } else {
+    if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
+    if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
+  }
 #pragma unroll
   for (int k = 0; k < 6; k++) { acc1[k] = 0.0; acc2[k] = 0.0; }
   // The chain over the contacts of a pair is sequential; the record of contact c+1 is loaded into a second register
@@ -882,8 +913,13 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (a >= 0) {
     if (!hubA) {
-      st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
-      st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
+      if (SM) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
+      } else {
+        st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
+        st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + k] = acc1[k];
@@ -891,8 +927,13 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (b >= 0) {
     if (!hubB) {
-      st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
-      st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
+      if (SM) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
+      } else {
+        st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
+        st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
+      }
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + 6 + k] = acc2[k];
@@ -1004,6 +1045,100 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batched scenes: ONE CTA PER SCENE.  Bodies of different scenes never interact, so a scene's solve needs no grid-wide
+// barrier: the CTA keeps the scene's deltaV in shared memory, walks the scene's phases with __syncthreads() between
+// them, and takes the tolerance exit of PGS.java:190-192 for ITS scene alone - exactly what the reference does when
+// it runs that scene on its own.  CTAs fetch scenes from a ticket counter.
+// iterState: [2] max iterations over scenes, [4] sum over scenes of contacts x iterations, [5] scene ticket
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hubReduceRunSm(int r, const HubRuns& H, const int* __restrict__ runLocal,
+                                               const double* __restrict__ hubDelta, double* __restrict__ sdv) {
+  int lane = threadIdx.x & 31;
+  int e0 = H.runStart[r], e1 = H.runStart[r + 1];
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  for (int e = e0 + lane; e < e1; e += 32) {
+    int slot = H.entrySlot[e];
+    const double* d = hubDelta + 6 * (size_t)slot;
+#pragma unroll
+    for (int k = 0; k < 6; k++) s[k] = s[k] + __ldcg(d + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+    for (int o = 16; o > 0; o >>= 1) s[k] = s[k] + __shfl_xor_sync(0xffffffffu, s[k], o);
+  if (lane == 0) {
+    int h = runLocal[r];
+#pragma unroll
+    for (int k = 0; k < 6; k++) sdv[6 * h + k] = sdv[6 * h + k] + s[k];
+  }
+}
+template <int MODE, bool HUB>
+__device__ __forceinline__ void scenePass(int ph0, int ph1, const int* __restrict__ phaseStart, const int* __restrict__ phaseRunStart,
+                                          const HubRuns& H, const int* __restrict__ runLocal, const SolveArrays& S, double* sdv,
+                                          const PgsParams& P, int last, double& localMax) {
+  int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int ph = ph0; ph < ph1; ph++) {
+    int g1 = phaseStart[ph + 1];
+    for (int p = phaseStart[ph] + threadIdx.x; p < g1; p += blockDim.x) pgsGroup<MODE, HUB, true>(p, S, sdv, P, last, localMax);
+    __syncthreads();
+    if (HUB) {
+      int r0 = phaseRunStart[ph], r1 = phaseRunStart[ph + 1];
+      if (r1 > r0) {
+        for (int r = r0 + warp; r < r1; r += nwarps) hubReduceRunSm(r, H, runLocal, S.hubDelta, sdv);
+        __syncthreads();
+      }
+    }
+  }
+}
+template <bool HUB>
+__global__ void __launch_bounds__(128)
+k_pgs_scene(int nScenes, int slotsPerScene, const int* __restrict__ sceneRange, const int* __restrict__ phaseStart,
+            const int* __restrict__ phaseRunStart, HubRuns H, const int* __restrict__ runLocal, SolveArrays S,
+            double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance, unsigned long long* __restrict__ iterState) {
+  extern __shared__ double sdv[];  // [slotsPerScene * 6]
+  __shared__ int sScene;
+  __shared__ double sMax[4];
+  for (;;) {
+    if (threadIdx.x == 0) sScene = (int)atomicAdd(iterState + 5, 1ULL);
+    __syncthreads();
+    int scene = sScene;
+    if (scene >= nScenes) return;
+    int ph0 = sceneRange[2 * scene], ph1 = sceneRange[2 * scene + 1];
+    for (int k = threadIdx.x; k < slotsPerScene * 6; k += blockDim.x) sdv[k] = 0.0;
+    __syncthreads();
+    if (ph1 > ph0) {
+      double dummy = 0;
+      scenePass<0, HUB>(ph0, ph1, phaseStart, phaseRunStart, H, runLocal, S, sdv, P, 0, dummy);
+      int done = 0;
+      for (int it = 0; it < iterations; it++) {
+        double localMax = 0;
+        scenePass<1, HUB>(ph0, ph1, phaseStart, phaseRunStart, H, runLocal, S, sdv, P, it == iterations - 1, localMax);
+        done = it + 1;
+        if (checkTolerance) {  // max |delta lambda| over the scene's contacts (PGS.java:125,159,176,190)
+          for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+          if ((threadIdx.x & 31) == 0) sMax[threadIdx.x >> 5] = localMax;
+          __syncthreads();
+          double m = fmax(fmax(sMax[0], sMax[1]), fmax(sMax[2], sMax[3]));
+          __syncthreads();
+          if (m < P.tolerance) break;
+        }
+      }
+      // hand the deltaV of the scene's solver bodies back (every group writes its two bodies: same values)
+      int gBeg = phaseStart[ph0], gEnd = phaseStart[ph1];
+      for (int p = gBeg + threadIdx.x; p < gEnd; p += blockDim.x) {
+        int a = S.sgB1[p], b = S.sgB2[p];
+        if (a >= 0) { const double* q = sdv + 6 * S.sgL1[p]; st4(dv + DVS * (size_t)a, q[0], q[1], q[2], q[3]); st4(dv + DVS * (size_t)a + 4, q[4], q[5], 0.0, 0.0); }
+        if (b >= 0) { const double* q = sdv + 6 * S.sgL2[p]; st4(dv + DVS * (size_t)b, q[0], q[1], q[2], q[3]); st4(dv + DVS * (size_t)b + 4, q[4], q[5], 0.0, 0.0); }
+      }
+      if (threadIdx.x == 0) {
+        atomicMax(iterState + 2, (unsigned long long)done);
+        atomicAdd(iterState + 4, (unsigned long long)(S.sgStart[gEnd - 1] + S.sgCount[gEnd - 1] - S.sgStart[gBeg]) * (unsigned long long)done);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // hub entries: one per (group, hub side), keyed (colour, hub body, group position) so that a radix sort groups them
 // into (colour, hub) runs with ascending group position
 __global__ void k_hub_entries(int ng, const int* __restrict__ sgFlags, const int* __restrict__ sgB1, const int* __restrict__ sgB2,
@@ -1029,13 +1164,16 @@ __global__ void k_hub_run_heads(int ne, const unsigned long long* __restrict__ k
   head[e] = (e == 0 || (key[e] >> 23) != (key[e - 1] >> 23)) ? 1 : 0;
 }
 __global__ void k_hub_run_fill(int ne, const unsigned long long* __restrict__ key, const int* __restrict__ head,
-                               const int* __restrict__ scan, int* __restrict__ runStart, int* __restrict__ runBody,
+                               const int* __restrict__ scan, const int* __restrict__ bodyLocal, const int* __restrict__ collRep, int nb,
+                               int* __restrict__ runStart, int* __restrict__ runBody, int* __restrict__ runLocal,
                                int* __restrict__ runColor) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne || !head[e]) return;
   int r = scan[e];
   runStart[r] = e;
-  runBody[r] = (int)((key[e] >> 23) & 0x7fffff);
+  int hb = (int)((key[e] >> 23) & 0x7fffff);
+  runLocal[r] = bodyLocal[hb < nb ? hb : collRep[hb - nb]];
+  runBody[r] = hb;
   runColor[r] = (int)(key[e] >> 46);
 }
 

@@ -79,20 +79,65 @@ def test_million_box_stack_invariants():
 
 
 def test_batched_copies_agree():
-    """config B: every copy is its own scene; copies only differ in Gauss-Seidel order (colour priorities hash the
-    group index), so before the towers collapse they agree to solver precision and they never interact."""
+    """config B: every copy is its own scene, coloured and solved (one CTA per scene, own tolerance exit) exactly as if it
+    were alone: identical copies stay bit-identical, and they never interact."""
     one = golden_scene("tower25platform")
     copies = 64
     blob = one.replicate(copies)
     p = apply_overrides(default_params(), one.overrides)
     s = RigidBodySystem(0).load(blob, p)
-    s.advanceTime(0.05, 40)
+    s.advanceTime(0.05, 140)
     b = s.bodies()
     nb = one.a["body_type"].shape[0]
-    x = b["x"].reshape(copies, nb, 3)
-    assert np.abs(x - x[0]).max() < 1e-3
+    for k in ("x", "R", "v", "omega"):
+        a = b[k].reshape(copies, nb, -1)
+        assert np.array_equal(a.view(np.uint64), np.broadcast_to(a[:1], a.shape).view(np.uint64)), k
     c = s.contacts()
     assert (c["body1"] // nb == c["body2"] // nb).all()  # no contact crosses scenes
     counts = np.bincount(c["body1"] // nb, minlength=copies)
-    assert counts.min() > 0 and counts.max() - counts.min() <= 0.05 * counts.max()
+    assert counts.min() == counts.max() > 0
     s.close()
+
+
+def test_scene_in_a_batch_equals_the_scene_alone():
+    """Scene k of a batched context == the same scene run alone in its own context, bit for bit: body states, contact
+    multipliers, merge / unmerge events and PGS iteration counts.  The copies get different initial kicks, so they
+    collapse differently and leave the PGS at different iteration counts (per-scene tolerance exit, PGS.java:190-192)."""
+    one = golden_scene("tower25platform")
+    copies, steps = 8, 170
+    nb = one.a["body_type"].shape[0]
+    p = apply_overrides(default_params(), one.overrides)
+    kicked = one.names.index("B3L0")
+
+    def kick(blob, scene, k):
+        v = blob.a["body_v"].reshape(-1, 3)
+        v[scene * nb + kicked] = (0.03 * k, 0.0, -0.02 * k)
+
+    batch = one.replicate(copies)
+    for k in range(copies):
+        kick(batch, k, k)
+    s = RigidBodySystem(0).load(batch, p)
+    s.advanceTime(0.05, steps)
+    bb, cb, eb = s.bodies(), s.contacts(), s.events()
+    s.close()
+    assert len(eb) > 0
+    for k in (0, 3, 7):
+        alone = one.replicate(1)
+        kick(alone, 0, k)
+        a = RigidBodySystem(0).load(alone, p)
+        a.advanceTime(0.05, steps)
+        ba, ca, ea = a.bodies(), a.contacts(), a.events()
+        a.close()
+        sl = slice(k * nb, (k + 1) * nb)
+        for f in ("x", "R", "v", "omega"):
+            assert np.array_equal(bb[f][sl].view(np.uint64), ba[f].view(np.uint64)), (k, f)
+        assert np.array_equal(bb["sleeping"][sl], ba["sleeping"])
+        mine = cb[(cb["body1"] // nb) == k]
+        assert len(mine) == len(ca)
+        assert np.array_equal(mine["lambda"].view(np.uint64), ca["lambda"].view(np.uint64)), k
+        ev = eb[(eb[:, 2] // nb) == k].copy()
+        ev[:, 2:] -= k * nb
+        assert sorted(map(tuple, ev.tolist())) == sorted(map(tuple, ea.tolist())), k
+    # the copies really differ
+    x = bb["x"].reshape(copies, nb, 3)
+    assert np.abs(x[7] - x[0]).max() > 1e-3
