@@ -319,12 +319,6 @@ int am3d_create(int device, am3d_ctx** out) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<false>, 128, 0)); c->coopBlocksV[0] = coop ? sms * perSm : 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<true>, 128, 0));  c->coopBlocksV[1] = coop ? sms * perSm : 0;
     c->coopBlocks = c->coopBlocksV[1];
-    {  // per-scene solve: up to 160 KB of shared memory for the deltaV table of a scene; co-residency for 16 KB (a 340-body scene)
-      CK(cudaFuncSetAttribute(k_pgs_scene<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      CK(cudaFuncSetAttribute(k_pgs_scene<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_scene<true>, 128, 16 * 1024));
-      c->sceneBlocks = sms * std::max(perSm, 1);
-    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_layers, 256, 0)); c->bfsBlocks = coop ? sms * perSm : 0;
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
   } catch (const AmError& e) {
@@ -706,7 +700,6 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   if (!strcmp(name, "hub_min_degree")) c->hubMin = (int)value;
   else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
   else if (!strcmp(name, "record_events")) c->recordEvents = value != 0;
-  else if (!strcmp(name, "pgs_per_scene")) c->useSceneSolve = (int)value;
   else if (!strcmp(name, "merge_exact_max_pairs")) c->mergeExactMax = (int)value;
   else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);
   API_END(c)

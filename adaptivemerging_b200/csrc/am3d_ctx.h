@@ -227,11 +227,9 @@ struct am3d_ctx {
   int mergeExactMax = 16384;  // mergeable pairs per component up to which the reference's visiting sequence is replayed
   DevBuf<int> swB1, swB2, swCount, swStart, swAsleep, tmpI2, tmpI3;
   DevBuf<int> grpLayer, bodyLevel, bfsRound;  // breadth-first layers of the single sweep (getOrganizedContacts)
-  DevBuf<int> bodyLocal, collRep, sgL1, sgL2, sceneRange, hubRunLocal;  // per-scene solve (one CTA per scene)
-  int maxSceneBodies = 0;   // largest number of bodies in one scene
-  int sceneBlocks = 0;      // co-resident CTAs of k_pgs_scene (0: per-scene solve not possible)
-  int useSceneSolve = 1;    // am3d_set_option("pgs_per_scene", 0/1)
-  bool sceneSolveActive = false;
+  DevBuf<int> bodyLocal;   // rank of a leaf body among the bodies of its scene (colour priorities hash scene-local ids)
+  DevBuf<int> sgScene;     // per solve group
+  DevBuf<int> sceneState;  // per scene: done | moving | iterations (the tolerance exit is taken per scene)
   DevBuf<int> phaseHead, phaseScan, sgPhase;  // (layer, colour) phases of the sorted group list
   int bfsBlocks = 0;
   bool orderingTimed = false;

@@ -65,11 +65,7 @@ static void resetState(am3d_ctx* c) {
   {  // scene-local body ids (rank of a body among the bodies of its scene)
     std::vector<int> cnt(H.nscenes, 0), loc(NB);
     for (int i = 0; i < NB; i++) loc[i] = cnt[H.body_scene[i]]++;
-    c->maxSceneBodies = 0;
-    for (int k = 0; k < H.nscenes; k++) c->maxSceneBodies = std::max(c->maxSceneBodies, cnt[k]);
     h2dv(c, c->bodyLocal, loc);
-    c->collRep.ensure(NC + 2);
-    CK(cudaMemsetAsync(c->collRep.p, 0, (NC + 2) * sizeof(int), c->stream));
   }
   h2dv(c, c->btype, padI(H.body_type, -1));
   h2dv(c, c->parent, padI(std::vector<int>(NB, -1), -1));

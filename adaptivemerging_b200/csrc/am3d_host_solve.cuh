@@ -5,7 +5,7 @@
 #include "am3d_step.cuh"
 
 static SolveArrays solveArrays(am3d_ctx* c) {
-  return SolveArrays{c->sgB1.p, c->sgB2.p, c->sgStart.p, c->sgCount.p, c->sgFlags.p, c->sgBpc.p, c->sgL1.p, c->sgL2.p, c->sgMass.p, c->sgMu.p,
+  return SolveArrays{c->sgB1.p, c->sgB2.p, c->sgStart.p, c->sgCount.p, c->sgFlags.p, c->sgBpc.p, c->sgScene.p, c->sceneState.p, c->sgMass.p, c->sgMu.p,
                      c->scP.p, c->scSrc.p, c->scState.p, c->hubDelta.p};
 }
 static ContactPtrs contactPtrs(ContactSet& S) {
@@ -51,13 +51,9 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
     LAUNCH(c, k_color_next_page, nblk(ng), BLK, ng, page - 1, c->grpColor.p);
   }
   int maxColors = (page + 1) * 64;
-  // one CTA per scene when the context holds several scenes whose deltaV tables fit shared memory
-  c->sceneSolveActive = c->useSceneSolve && c->H.nscenes > 1 && c->sceneBlocks > 0 && (size_t)c->maxSceneBodies * 48 <= 160 * 1024;
-  int sceneShift = 0;
   int endBit = 20 + (layer ? layerBits : 0);
   if (!layer) endBit = 8 + bitsFor((unsigned long long)maxColors);
-  if (c->sceneSolveActive) { sceneShift = endBit; endBit += bitsFor((unsigned long long)c->H.nscenes); }
-  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, gb1, c->scene.p, sceneShift, c->grpKey.p, c->grpVal.p);
+  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, c->grpKey.p, c->grpVal.p);
   cubRun(c, [&](void* t, size_t& b) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
   });
@@ -65,7 +61,6 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   c->phaseHead.ensure(ng + 2); c->phaseScan.ensure(ng + 2); c->sgPhase.ensure(ng + 2);
   LAUNCH(c, k_phase_heads, nblk(ng), BLK, ng, c->grpKeySorted.p, c->phaseHead.p);
   int nPhases = scanTotal(c, c->phaseHead, c->phaseScan, ng);
-  if (nPhases >= (1 << 18)) throw AmError(AM3D_ECAPACITY, "more than 262143 solve phases");
   c->dColorStart.ensure(nPhases + 2);
   LAUNCH(c, k_phase_fill, nblk(ng), BLK, ng, c->phaseHead.p, c->phaseScan.p, c->dColorStart.p, c->sgPhase.p);
   c->colorStart.resize(nPhases + 1);
@@ -73,11 +68,6 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   CK(cudaStreamSynchronize(c->stream));
   c->nColors = nPhases;
   c->nGroups = ng;
-  if (c->sceneSolveActive) {
-    c->sceneRange.ensure(2 * (size_t)c->H.nscenes + 2);
-    CK(cudaMemsetAsync(c->sceneRange.p, 0, 2 * (size_t)c->H.nscenes * sizeof(int), c->stream));
-    LAUNCH(c, k_scene_phases, nblk(nPhases), BLK, nPhases, c->dColorStart.p, c->grpKeySorted.p, sceneShift, c->sceneRange.p);
-  }
 }
 
 // One contact set taking part in a solve: its groups start at groupOffset in the group list.
@@ -145,11 +135,13 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   }
   colourGroups(c, ng, gb1, gb2, gcount, sweep ? 1 : 0, layer, layerBits);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
-  c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1); c->sgL1.ensure(ng + 1); c->sgL2.ensure(ng + 1);
+  c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1); c->sgScene.ensure(ng + 1);
+  int nScenes = c->H.nscenes;
+  c->sceneState.ensure((2 + MV_SLOTS) * (size_t)nScenes + 1);
   c->scP.ensure(24 * (size_t)nc + 48); c->scSrc.ensure(nc + 1); c->scState.ensure(nc + 1); c->hubDelta.ensure(12 * (size_t)ng + 12);
   SolveArrays S = solveArrays(c);
   LAUNCH(c, k_group_setup, nblk(ng), BLK, ng, c->grpOrder.p, c->grpSb1.p, c->grpSb2.p, gb1, gb2, gcount, c->minv.p, c->jinv.p,
-         c->fric.p, c->flags.p, c->grpHubMask.p, P.friction_override, P.friction, c->bodyLocal.p, c->collRep.p, c->NB, S, c->grpPos.p);
+         c->fric.p, c->flags.p, c->grpHubMask.p, P.friction_override, P.friction, c->scene.p, S, c->grpPos.p);
   int nSolve = scanTotal(c, c->sgCount, c->sgStart, ng);  // contacts that take part (sleeping collections excluded)
   c->lastSolveN = nSolve;
   // hub runs: (colour, hub body) -> the groups of that colour touching the hub, ascending
@@ -161,18 +153,19 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     int ne = scanTotal(c, c->hubN, c->hubScan, ng);
     c->nHubEntries = ne;
     c->hubKey.ensure(ne + 2); c->hubKeySorted.ensure(ne + 2); c->hubSlot.ensure(ne + 2); c->hubSlotSorted.ensure(ne + 2);
-    c->hubHead.ensure(ne + 2); c->hubRunStart.ensure(ne + 2); c->hubRunBody.ensure(ne + 2); c->hubRunColor.ensure(ne + 2); c->hubRunLocal.ensure(ne + 2);
-    if (ng >= (1 << 23) || c->NS >= (1 << 23)) throw AmError(AM3D_ECAPACITY, "hub runs support up to 8M groups / solver bodies");
-    LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgPhase.p, c->hubScan.p,
+    c->hubHead.ensure(ne + 2); c->hubRunStart.ensure(ne + 2); c->hubRunBody.ensure(ne + 2); c->hubRunColor.ensure(ne + 2);
+    int bitsG = bitsFor((unsigned long long)ng), bitsB = bitsFor((unsigned long long)c->NS), bitsP = bitsFor((unsigned long long)c->nColors);
+    if (bitsG + bitsB + bitsP > 64) throw AmError(AM3D_ECAPACITY, "hub run keys: groups x solver bodies x phases exceed 64 bits");
+    LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgPhase.p, c->hubScan.p, bitsG, bitsB,
            c->hubKey.p, c->hubSlot.p);
     cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, 64, c->stream);
+      return cub::DeviceRadixSort::SortPairs(t, b, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, bitsG + bitsB + bitsP, c->stream);
     });
-    LAUNCH(c, k_hub_run_heads, nblk(ne), BLK, ne, c->hubKeySorted.p, c->hubHead.p);
+    LAUNCH(c, k_hub_run_heads, nblk(ne), BLK, ne, c->hubKeySorted.p, bitsG, c->hubHead.p);
     int nr = scanTotal(c, c->hubHead, c->hubScan, ne);
     c->nHubRuns = nr;
-    LAUNCH(c, k_hub_run_fill, nblk(ne), BLK, ne, c->hubKeySorted.p, c->hubHead.p, c->hubScan.p, c->bodyLocal.p, c->collRep.p, c->NB,
-           c->hubRunStart.p, c->hubRunBody.p, c->hubRunLocal.p, c->hubRunColor.p);
+    LAUNCH(c, k_hub_run_fill, nblk(ne), BLK, ne, c->hubKeySorted.p, c->hubHead.p, c->hubScan.p, bitsG, bitsB, c->hubRunStart.p, c->hubRunBody.p,
+           c->hubRunColor.p);
     CK(cudaMemcpyAsync(c->hubRunStart.p + nr, &c->nHubEntries, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     std::vector<int> rc(nr);
     CK(cudaMemcpyAsync(rc.data(), c->hubRunColor.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -194,30 +187,19 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
            CS.t1B1.p, CS.t2B1.p, CS.viol.p, CS.lam.p, CS.state.p, c->x.p, c->R.p, c->v.p, c->w.p, c->force.p, c->torque.p,
            c->minv.p, c->jinv.p, c->rest.p, dt, P.feedback_stiffness, P.restitution_override, P.restitution, S);
   }
-  CK(cudaMemsetAsync(c->iterState.p, 0, 8 * sizeof(unsigned long long), c->stream));
-  PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold};
+  // iterState: [1] every scene done, [2] largest iteration count, [4] contact-iterations, [6] scenes still iterating
+  unsigned long long is0[8] = {0, 0, 0, 0, 0, 0, (unsigned long long)nScenes, 0};
+  CK(cudaMemcpyAsync(c->iterState.p, is0, sizeof(is0), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->sceneState.p, 0, (2 + MV_SLOTS) * (size_t)nScenes * sizeof(int), c->stream));
+  PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold, nScenes, sweep ? 0 : 1};
   int iterations = sweep ? P.iterations_in_collection : P.iterations;
   CK(cudaEventRecord(c->ev[sweep ? 8 : 10], c->stream));
   // many small colours (hubs, batched scenes): one cooperative launch with grid barriers; few large colours: one
   // launch per colour (no barrier cost, full occupancy per launch)
   long long avgGroups = ng / std::max(1, c->nColors);
   bool persistent = c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
-  if (c->sceneSolveActive) {
-    int nScenes = c->H.nscenes, slots = c->maxSceneBodies, chk = sweep ? 0 : 1;
-    bool hubs = c->nHubRuns > 0;
-    if (hubs) {
-      c->dColorRunStart.ensure(c->colorRunStart.size() + 1);
-      CK(cudaMemcpyAsync(c->dColorRunStart.p, c->colorRunStart.data(), c->colorRunStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    }
-    size_t smem = (size_t)slots * 6 * sizeof(double);
-    int grid = std::min(nScenes, c->sceneBlocks);
-    if (hubs) k_pgs_scene<true><<<grid, 128, smem, c->stream>>>(nScenes, slots, c->sceneRange.p, c->dColorStart.p, c->dColorRunStart.p, HR, c->hubRunLocal.p, S, c->dv.p, PP, iterations, chk, c->iterState.p);
-    else k_pgs_scene<false><<<grid, 128, smem, c->stream>>>(nScenes, slots, c->sceneRange.p, c->dColorStart.p, nullptr, HR, c->hubRunLocal.p, S, c->dv.p, PP, iterations, chk, c->iterState.p);
-    CK(cudaGetLastError());
-    c->kernelLaunches++;
-    if (!sweep) c->solveLaunches++;
-  } else if (persistent) {
-    int nColors = c->nColors, chk = sweep ? 0 : 1;
+  if (persistent) {
+    int nColors = c->nColors;
     const int* dcs = c->dColorStart.p;
     const int* dcr = nullptr;
     if (c->nHubRuns > 0) {
@@ -227,7 +209,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     }
     double* dvp = c->dv.p;
     unsigned long long* isp = c->iterState.p;
-    void* args[] = {&nColors, &dcs, &dcr, &HR, &S, &dvp, &PP, &iterations, &chk, &isp};
+    void* args[] = {&nColors, &dcs, &dcr, &HR, &S, &dvp, &PP, &iterations, &isp};
     bool hubs = c->nHubRuns > 0;
     const void* kfn = hubs ? (const void*)k_pgs_persistent<true> : (const void*)k_pgs_persistent<false>;
     CK(cudaLaunchCooperativeKernel(kfn, dim3(c->coopBlocksV[hubs ? 1 : 0]), dim3(128), args, 0, c->stream));
@@ -238,7 +220,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
       LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
       int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
-      if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 0);
+      if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 0, 0);
     }
     for (int it = 0; it < iterations; it++) {
       int last = it == iterations - 1;
@@ -247,10 +229,10 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
         if (c->nHubRuns > 0) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         else LAUNCH(c, (k_pgs_color<1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
-        if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, c->hubDelta.p, c->dv.p, c->iterState.p, 1);
+        if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 1, PP.check);
         if (!sweep) c->solveLaunches++;
       }
-      LAUNCH(c, k_iter_end, 1, 1, c->iterState.p, PP.tolerance, sweep ? 0 : 1);
+      LAUNCH(c, k_iter_end, nblk(nScenes), BLK, S, PP, c->iterState.p);
     }
   }
   CK(cudaEventRecord(c->ev[sweep ? 9 : 11], c->stream));
@@ -263,6 +245,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     if (nSolve) CK(cudaMemcpyAsync(dst.data(), c->scSrc.p, nSolve * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
   if (!sweep) {
+    LAUNCH(c, k_row_updates, nblk(ng), BLK, ng, S, nScenes, c->iterState.p);
     unsigned long long st[5];
     CK(cudaMemcpyAsync(st, c->iterState.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -271,7 +254,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]));
     c->T.pgs_kernel_time = ms * 1e-3;
-    c->rowUpdates += c->sceneSolveActive ? 3.0 * (double)st[4] : 3.0 * nSolve * (double)st[2];
+    c->rowUpdates += 3.0 * (double)st[4];
     c->solveSeconds += c->T.pgs_kernel_time;
   } else {
     CK(cudaStreamSynchronize(c->stream));
@@ -291,7 +274,6 @@ static void rebuildMembers(am3d_ctx* c) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->memKey.p, c->memKeySorted.p, c->memVal.p, c->members.p, nb, 0, bitsFor((unsigned long long)nc + 1), c->stream);
   });
   c->nMergedLeaves = scanTotal(c, c->collCount, c->collStart, nc);
-  LAUNCH(c, k_coll_rep, nblk(nc), BLK, nc, c->collStart.p, c->collCount.p, c->members.p, c->collRep.p);
 }
 static int countAlive(am3d_ctx* c) {
   int nc = c->NS - c->NB;

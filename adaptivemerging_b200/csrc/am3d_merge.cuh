@@ -313,13 +313,6 @@ __global__ void k_member_keys(int nb, int nc, const int* __restrict__ parent, un
   if (p >= 0) atomicAdd(collCount + (p - nb), 1);
 }
 
-// first member (lowest leaf id) of every collection: its scene-local id is the collection's deltaV slot in the
-// per-scene solve
-__global__ void k_coll_rep(int nc, const int* __restrict__ collStart, const int* __restrict__ collCount,
-                           const int* __restrict__ members, int* __restrict__ collRep) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < nc) collRep[c] = collCount[c] > 0 ? members[collStart[c]] : 0;
-}
 // ------------------------------------------------------------------------------------------------
 // collection mass properties: one block per changed collection
 // ------------------------------------------------------------------------------------------------

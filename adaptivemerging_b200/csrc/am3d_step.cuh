@@ -583,27 +583,13 @@ __global__ void k_color_next_page(int ng, int page, int* __restrict__ color) {
 // share no free body) by descending contact count so that the lanes of a warp run the same number of contacts; ties by
 // group index (the radix sort is stable).  layer = breadth-first distance from the body pairs that hold new contacts
 // (getOrganizedContacts, CollisionProcessor.java:346-441) for the single sweep, absent (0) for the full solve.
-// With sceneShift > 0 (batched scenes solved one CTA per scene) the scene id leads the key, so that every scene's
-// phases are contiguous.
 __global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount, const int* __restrict__ layer,
-                                const int* __restrict__ gb1, const int* __restrict__ bodyScene, int sceneShift,
                                 unsigned long long* __restrict__ key, int* __restrict__ val) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   unsigned long long L = layer ? (unsigned long long)(unsigned)layer[g] : 0ULL;
-  unsigned long long k = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
-  if (sceneShift > 0) k |= (unsigned long long)(unsigned)bodyScene[gb1[g]] << sceneShift;
-  key[g] = k;
+  key[g] = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
   val[g] = g;
-}
-// per scene: its range of phases (scenes without groups keep start = end = 0)
-__global__ void k_scene_phases(int nPhases, const int* __restrict__ phaseStart, const unsigned long long* __restrict__ key,
-                               int sceneShift, int* __restrict__ sceneRange /* [2 * nScenes] */) {
-  int ph = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ph >= nPhases) return;
-  int s = (int)(key[phaseStart[ph]] >> sceneShift);
-  if (ph == 0 || (int)(key[phaseStart[ph - 1]] >> sceneShift) != s) sceneRange[2 * s] = ph;
-  if (ph == nPhases - 1 || (int)(key[phaseStart[ph + 1]] >> sceneShift) != s) sceneRange[2 * s + 1] = ph + 1;
 }
 // phases of the sorted group list: head = first group of a (layer, colour) class
 __global__ void k_phase_heads(int ng, const unsigned long long* __restrict__ key, int* __restrict__ head) {
@@ -626,7 +612,8 @@ __global__ void k_phase_fill(int ng, const int* __restrict__ head, const int* __
 // ------------------------------------------------------------------------------------------------
 struct SolveArrays {
   int *sgB1, *sgB2, *sgStart, *sgCount, *sgFlags, *sgBpc;
-  int *sgL1, *sgL2;  // scene-local deltaV slots of the two solver bodies (per-scene solve), -1 = pinned
+  int* sgScene;      // scene of the group (a context can hold many independent scenes)
+  int* sceneState;   // done[nScenes] | iterations executed[nScenes] | still moving in this iteration[nScenes][MV_SLOTS]  (PGS.java:190-192 per scene)
   double *sgMass, *sgMu;
   double* scP;       // [24] per contact, solve order: n t1 t2 (9) | r1 r2 (6) | b (3) | D (3) | lambda (3)
   int *scSrc, *scState;
@@ -642,8 +629,7 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
                               const int* __restrict__ gcount, const double* __restrict__ minv,
                               const double* __restrict__ jinv, const double* __restrict__ fric,
                               const int* __restrict__ flags, const int* __restrict__ hubMask, int frictionOverride,
-                              double frictionVal, const int* __restrict__ bodyLocal, const int* __restrict__ collRep, int nb,
-                              SolveArrays S, int* __restrict__ grpPos) {
+                              double frictionVal, const int* __restrict__ bodyScene, SolveArrays S, int* __restrict__ grpPos) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ng) return;
   int g = order[p];
@@ -652,10 +638,7 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
   int ia = a >= 0 ? a : -1 - a, ib = b >= 0 ? b : -1 - b;
   S.sgB1[p] = a >= 0 ? a : -1;
   S.sgB2[p] = b >= 0 ? b : -1;
-  // deltaV slot inside the scene: a leaf uses its scene-local id, a collection the id of its first member (which,
-  // being merged, is no solver body of this solve itself)
-  S.sgL1[p] = a >= 0 ? bodyLocal[a < nb ? a : collRep[a - nb]] : -1;
-  S.sgL2[p] = b >= 0 ? bodyLocal[b < nb ? b : collRep[b - nb]] : -1;
+  S.sgScene[p] = bodyScene[gb1[g]];
   S.sgCount[p] = gcount[g];
   S.sgBpc[p] = g;
   double* M = S.sgMass + 20 * p;
@@ -779,8 +762,11 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
 // ------------------------------------------------------------------------------------------------
 // PGS sweeps: one launch per colour, one thread per body-pair group, the group's contacts in sequence
 // ------------------------------------------------------------------------------------------------
+#define MV_SLOTS 32  // "still moving" flags per scene, spread over CTAs so that a single-scene context does not hammer one address
 struct PgsParams {
   double omega, compliance, tolerance, sliding;
+  int nScenes;  // sceneState = done[nScenes] | iterations[nScenes] | moving[nScenes][MV_SLOTS]
+  int check;    // take the tolerance exit (full solve) or not (single sweep)
 };
 
 __device__ __forceinline__ double dot6(const d3& jv, const d3& jw, const double* dvp) {
@@ -804,11 +790,45 @@ __device__ __forceinline__ void applyRow(double* dvp, double minv, const double*
 // A hub side works on a private copy of the hub's deltaV as of the start of the colour (plus this group's own
 // updates) and hands what it added to hubDelta; k_hub_reduce folds the deltas in after the colour, in a fixed order.
 __device__ __forceinline__ void prefetchL2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// SM = true: dv is the CTA's shared-memory deltaV table of one scene (6 doubles per scene-local slot).
-template <int MODE, bool HUB, bool SM = false>
-__device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter,
-                                         double& localMax) {
-  int a = SM ? S.sgL1[p] : S.sgB1[p], b = SM ? S.sgL2[p] : S.sgB2[p];
+// a / b, correctly rounded, from y = RN(1/b): q = a*y is within an ulp or two of the quotient, and each step
+// q <- fma(fma(-b, q, a), y, q) keeps or improves it; once q is a faithful rounding the step returns RN(a/b) exactly
+// (Markstein's theorem, the exact residual comes from the fused multiply-add).  600 M random and adversarial operand
+// pairs against the IEEE division: no mismatch already after ONE step; two are taken.  Zero numerators keep their
+// sign through a*y; results outside the normal range (underflow, overflow, NaN, y not finite) take the IEEE division.
+// Why: the division of the row update sits on the dependent chain of a group, where the IEEE sequence (reciprocal
+// seed + Newton steps + fix-up) costs ~30 dependent instructions; 1/b does not depend on the chain.
+__device__ __forceinline__ double divExact(double a, double b, double y) {
+  double q = a * y;
+  if (a == 0.0) return q;
+  double r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, y, q);
+  r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, y, q);
+  double m = fabs(q);
+  if (!(m > 1e-280 && m < 1e280)) q = a / b;
+  return q;
+}
+// The tolerance exit of PGS.java:190-192 is taken PER SCENE: a context can hold many independent scenes (batched
+// copies), and each of them leaves the iteration when ITS largest |delta lambda| falls below the tolerance, exactly as
+// if it were solved alone.  A group whose |delta lambda| stays at or above the tolerance marks its scene as moving;
+// scenes nobody marked are done after the iteration (k_iter_end / the persistent kernel) and their groups are skipped.
+// (Measured and not kept: two lanes per group, one per body, meeting through a shuffle per row - halves the serial
+// instruction stream of a group but doubles the load instructions and the redundant lambda arithmetic: slower on
+// both the batched scenes and the 1M-box stack; staging a scene's records through shared memory with bulk copies
+// (cp.async.bulk + mbarrier, 2 x 90 KB stages, one CTA per SM) removes the memory stalls but leaves one scene per
+// SM: 3.5x slower than two register-heavy CTAs per SM.  ncu: the sweep is bound by the dependent FP64 instruction
+// stream of a group, ~600 instructions per contact at one issue per ~5.6 cycles.  One CTA per scene with the scene's
+// deltaV in shared memory and __syncthreads() for grid barriers: 1.4x slower at 512 scenes per GPU, 2.2x slower at
+// 4096 than the grid-wide sweeps, which keep every SM busy with whatever scene has work.)
+template <int MODE, bool HUB>
+__device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter) {
+  int scene = 0;
+  if (MODE == 1 && P.check) {
+    scene = S.sgScene[p];
+    if (S.sceneState[scene]) return;  // this scene has left the iteration
+  }
+  double localMax = 0;
+  int a = S.sgB1[p], b = S.sgB2[p];
   int start = S.sgStart[p], cnt = S.sgCount[p];
   const double* PK0 = S.scP + 24 * (size_t)start;
   if (cnt > 0) { prefetchL2(PK0); prefetchL2(PK0 + 16); }
@@ -823,13 +843,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
   for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
-  if (SM) {
-#pragma unroll
-    for (int k = 0; k < 6; k++) { if (a >= 0) dv1[k] = dv[6 * a + k]; if (b >= 0) dv2[k] = dv[6 * b + k]; }
-  } else {
-    if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
-    if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
-  }
+  if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
+  if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
 #pragma unroll
   for (int k = 0; k < 6; k++) { acc1[k] = 0.0; acc2[k] = 0.0; }
   // The chain over the contacts of a pair is sequential; the record of contact c+1 is loaded into a second register
@@ -869,12 +884,15 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
     } else {
       double bb[3] = {Q[15], Q[16], Q[17]};
       double DD[3] = {Q[18], Q[19], Q[20]};
+      double den[3], y[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { den[k] = DD[k] + P.compliance; y[k] = 1.0 / den[k]; }  // off the dependent chain
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
         double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
         double prev = lam[k];
-        double l = (DD[k] * prev - P.omega * (bb[k] + Jdv)) / (DD[k] + P.compliance);
+        double l = divExact(DD[k] * prev - P.omega * (bb[k] + Jdv), den[k], y[k]);
         if (clamp) {
           if (k == 0) l = fmax(0.0, l);
           else {
@@ -913,13 +931,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (a >= 0) {
     if (!hubA) {
-      if (SM) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) dv[6 * a + k] = dv1[k];
-      } else {
-        st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
-        st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
-      }
+      st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
+      st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + k] = acc1[k];
@@ -927,17 +940,39 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   }
   if (b >= 0) {
     if (!hubB) {
-      if (SM) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) dv[6 * b + k] = dv2[k];
-      } else {
-        st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
-        st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
-      }
+      st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
+      st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
     } else {
 #pragma unroll
       for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + 6 + k] = acc2[k];
     }
+  }
+  // |delta lambda| >= tolerance somewhere in this group: its scene iterates on (written as "not below" so that a NaN
+  // keeps iterating, as Math.max / < do in PGS.java:176,190)
+  if (MODE == 1 && P.check) {
+    bool moving = !(localMax < P.tolerance);
+    unsigned act = __activemask();
+    unsigned peers = __match_any_sync(act, scene);           // lanes of this warp that hold a group of the same scene
+    bool any = (__ballot_sync(act, moving) & peers) != 0u;
+    if (any && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {  // one lane per scene and warp
+      int* f = S.sceneState + 2 * P.nScenes + (size_t)scene * MV_SLOTS + (blockIdx.x & (MV_SLOTS - 1));
+      if (!__ldcg(f)) *f = 1;
+    }
+  }
+}
+// end of an iteration, one thread per scene: count it, and retire the scenes nobody marked as moving
+// iterState: [1] every scene is done, [2] largest iteration count, [6] scenes still iterating
+__device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __restrict__ sceneState, unsigned long long* __restrict__ iterState) {
+  if (sceneState[s]) return;
+  int it = ++sceneState[P.nScenes + s];
+  atomicMax(iterState + 2, (unsigned long long)it);
+  int* mv = sceneState + 2 * P.nScenes + (size_t)s * MV_SLOTS;
+  int moving = 0;
+#pragma unroll 4
+  for (int k = 0; k < MV_SLOTS; k++) { moving |= __ldcg(mv + k); mv[k] = 0; }
+  if (P.check && !moving) {
+    sceneState[s] = 1;
+    if (atomicAdd(iterState + 6, (unsigned long long)-1LL) == 1ULL) iterState[1] = 1;
   }
 }
 
@@ -948,8 +983,11 @@ struct HubRuns {
   const int* runBody;    // [nRuns] hub solver body
   const int* entrySlot;  // group * 2 + side, ascending group within a run
 };
-__device__ __forceinline__ void hubReduceRun(int r, const HubRuns& H, const double* __restrict__ hubDelta, double* __restrict__ dv) {
+// sceneDone: the done flags of the scenes during the sweeps (a retired scene's groups wrote no deltas), or nullptr
+__device__ __forceinline__ void hubReduceRun(int r, const HubRuns& H, const double* __restrict__ hubDelta, double* __restrict__ dv,
+                                             const int* __restrict__ sgScene, const int* __restrict__ sceneDone) {
   int lane = threadIdx.x & 31;
+  if (sceneDone && sceneDone[sgScene[H.entrySlot[H.runStart[r]] >> 1]]) return;
   int e0 = H.runStart[r], e1 = H.runStart[r + 1];
   double s[6] = {0, 0, 0, 0, 0, 0};
   for (int e = e0 + lane; e < e1; e += 32) {
@@ -967,26 +1005,20 @@ __device__ __forceinline__ void hubReduceRun(int r, const HubRuns& H, const doub
     for (int k = 0; k < 6; k++) dv[DVS * (size_t)h + k] = __ldcg(dv + DVS * (size_t)h + k) + s[k];
   }
 }
-__global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, const double* __restrict__ hubDelta, double* __restrict__ dv,
-                             const unsigned long long* __restrict__ iterState, int mode) {
+__global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, SolveArrays S, double* __restrict__ dv,
+                             const unsigned long long* __restrict__ iterState, int mode, int check) {
   if (mode == 1 && iterState[1]) return;
   int r = rBegin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (r < rEnd) hubReduceRun(r, H, hubDelta, dv);
+  if (r < rEnd) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, (mode == 1 && check) ? S.sceneState : nullptr);
 }
 
 template <int MODE, bool HUB>
 __global__ void __launch_bounds__(128)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
             unsigned long long* __restrict__ iterState) {
-  if (MODE == 1 && iterState[1]) return;  // tolerance exit already taken (PGS.java:190-192)
+  if (MODE == 1 && iterState[1]) return;  // every scene has taken its tolerance exit (PGS.java:190-192)
   int p = gBegin + blockIdx.x * blockDim.x + threadIdx.x;
-  double localMax = 0;
-  if (p < gEnd) pgsGroup<MODE, HUB>(p, S, dv, P, lastIter, localMax);
-  if (MODE == 1) {
-    // max |delta lambda| of the sweep (PGS.java:125,159,176): non-negative doubles order like their bit patterns
-    for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
-    if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
-  }
+  if (p < gEnd) pgsGroup<MODE, HUB>(p, S, dv, P, lastIter);
 }
 
 // The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
@@ -997,160 +1029,67 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
 template <bool HUB>
 __global__ void __launch_bounds__(128)
 k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H,
-                 SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance,
-                 unsigned long long* __restrict__ iterState) {
+                 SolveArrays S, double* __restrict__ dv, PgsParams P, int iterations, unsigned long long* __restrict__ iterState) {
   cg::grid_group grid = cg::this_grid();
   int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   int warp = tid >> 5, nwarps = stride >> 5;
-  double dummy = 0;
   for (int c = 0; c < nColors; c++) {
     int g1 = colorStart[c + 1];
-    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0, HUB>(p, S, dv, P, 0, dummy);
+    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0, HUB>(p, S, dv, P, 0);
     grid.sync();
     if (HUB) {
       int r1 = colorRunStart[c + 1];
       if (r1 > colorRunStart[c]) {
-        for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);
+        for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, nullptr);
         grid.sync();
       }
     }
   }
   for (int it = 0; it < iterations; it++) {
     int last = it == iterations - 1;
-    double localMax = 0;
     for (int c = 0; c < nColors; c++) {
       int g1 = colorStart[c + 1];
-      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1, HUB>(p, S, dv, P, last, localMax);
+      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1, HUB>(p, S, dv, P, last);
       grid.sync();
       if (HUB) {
         int r1 = colorRunStart[c + 1];
         if (r1 > colorRunStart[c]) {
-          for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv);
+          for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, P.check ? S.sceneState : nullptr);
           grid.sync();
         }
       }
     }
-    for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
-    if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(iterState, (unsigned long long)__double_as_longlong(localMax));
-    grid.sync();
-    if (tid == 0) {
-      iterState[2] += 1;
-      double m = __longlong_as_double((long long)iterState[0]);
-      if (checkTolerance && m < P.tolerance) iterState[1] = 1;
-      iterState[3] = iterState[0];
-      iterState[0] = 0;
-    }
+    for (int s = tid; s < P.nScenes; s += stride) sceneIterEnd(s, P, S.sceneState, iterState);
     grid.sync();
     if (((volatile unsigned long long*)iterState)[1]) break;
   }
 }
-
-// ------------------------------------------------------------------------------------------------
-// Batched scenes: ONE CTA PER SCENE.  Bodies of different scenes never interact, so a scene's solve needs no grid-wide
-// barrier: the CTA keeps the scene's deltaV in shared memory, walks the scene's phases with __syncthreads() between
-// them, and takes the tolerance exit of PGS.java:190-192 for ITS scene alone - exactly what the reference does when
-// it runs that scene on its own.  CTAs fetch scenes from a ticket counter.
-// iterState: [2] max iterations over scenes, [4] sum over scenes of contacts x iterations, [5] scene ticket
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void hubReduceRunSm(int r, const HubRuns& H, const int* __restrict__ runLocal,
-                                               const double* __restrict__ hubDelta, double* __restrict__ sdv) {
-  int lane = threadIdx.x & 31;
-  int e0 = H.runStart[r], e1 = H.runStart[r + 1];
-  double s[6] = {0, 0, 0, 0, 0, 0};
-  for (int e = e0 + lane; e < e1; e += 32) {
-    int slot = H.entrySlot[e];
-    const double* d = hubDelta + 6 * (size_t)slot;
-#pragma unroll
-    for (int k = 0; k < 6; k++) s[k] = s[k] + __ldcg(d + k);
-  }
-#pragma unroll
-  for (int k = 0; k < 6; k++)
-    for (int o = 16; o > 0; o >>= 1) s[k] = s[k] + __shfl_xor_sync(0xffffffffu, s[k], o);
-  if (lane == 0) {
-    int h = runLocal[r];
-#pragma unroll
-    for (int k = 0; k < 6; k++) sdv[6 * h + k] = sdv[6 * h + k] + s[k];
-  }
+__global__ void k_iter_end(SolveArrays S, PgsParams P, unsigned long long* __restrict__ iterState) {
+  if (iterState[1]) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P.nScenes) sceneIterEnd(s, P, S.sceneState, iterState);
 }
-template <int MODE, bool HUB>
-__device__ __forceinline__ void scenePass(int ph0, int ph1, const int* __restrict__ phaseStart, const int* __restrict__ phaseRunStart,
-                                          const HubRuns& H, const int* __restrict__ runLocal, const SolveArrays& S, double* sdv,
-                                          const PgsParams& P, int last, double& localMax) {
-  int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int ph = ph0; ph < ph1; ph++) {
-    int g1 = phaseStart[ph + 1];
-    for (int p = phaseStart[ph] + threadIdx.x; p < g1; p += blockDim.x) pgsGroup<MODE, HUB, true>(p, S, sdv, P, last, localMax);
-    __syncthreads();
-    if (HUB) {
-      int r0 = phaseRunStart[ph], r1 = phaseRunStart[ph + 1];
-      if (r1 > r0) {
-        for (int r = r0 + warp; r < r1; r += nwarps) hubReduceRunSm(r, H, runLocal, S.hubDelta, sdv);
-        __syncthreads();
-      }
-    }
-  }
-}
-template <bool HUB>
-__global__ void __launch_bounds__(128)
-k_pgs_scene(int nScenes, int slotsPerScene, const int* __restrict__ sceneRange, const int* __restrict__ phaseStart,
-            const int* __restrict__ phaseRunStart, HubRuns H, const int* __restrict__ runLocal, SolveArrays S,
-            double* __restrict__ dv, PgsParams P, int iterations, int checkTolerance, unsigned long long* __restrict__ iterState) {
-  extern __shared__ double sdv[];  // [slotsPerScene * 6]
-  __shared__ int sScene;
-  __shared__ double sMax[4];
-  for (;;) {
-    if (threadIdx.x == 0) sScene = (int)atomicAdd(iterState + 5, 1ULL);
-    __syncthreads();
-    int scene = sScene;
-    if (scene >= nScenes) return;
-    int ph0 = sceneRange[2 * scene], ph1 = sceneRange[2 * scene + 1];
-    for (int k = threadIdx.x; k < slotsPerScene * 6; k += blockDim.x) sdv[k] = 0.0;
-    __syncthreads();
-    if (ph1 > ph0) {
-      double dummy = 0;
-      scenePass<0, HUB>(ph0, ph1, phaseStart, phaseRunStart, H, runLocal, S, sdv, P, 0, dummy);
-      int done = 0;
-      for (int it = 0; it < iterations; it++) {
-        double localMax = 0;
-        scenePass<1, HUB>(ph0, ph1, phaseStart, phaseRunStart, H, runLocal, S, sdv, P, it == iterations - 1, localMax);
-        done = it + 1;
-        if (checkTolerance) {  // max |delta lambda| over the scene's contacts (PGS.java:125,159,176,190)
-          for (int o = 16; o > 0; o >>= 1) localMax = fmax(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
-          if ((threadIdx.x & 31) == 0) sMax[threadIdx.x >> 5] = localMax;
-          __syncthreads();
-          double m = fmax(fmax(sMax[0], sMax[1]), fmax(sMax[2], sMax[3]));
-          __syncthreads();
-          if (m < P.tolerance) break;
-        }
-      }
-      // hand the deltaV of the scene's solver bodies back (every group writes its two bodies: same values)
-      int gBeg = phaseStart[ph0], gEnd = phaseStart[ph1];
-      for (int p = gBeg + threadIdx.x; p < gEnd; p += blockDim.x) {
-        int a = S.sgB1[p], b = S.sgB2[p];
-        if (a >= 0) { const double* q = sdv + 6 * S.sgL1[p]; st4(dv + DVS * (size_t)a, q[0], q[1], q[2], q[3]); st4(dv + DVS * (size_t)a + 4, q[4], q[5], 0.0, 0.0); }
-        if (b >= 0) { const double* q = sdv + 6 * S.sgL2[p]; st4(dv + DVS * (size_t)b, q[0], q[1], q[2], q[3]); st4(dv + DVS * (size_t)b + 4, q[4], q[5], 0.0, 0.0); }
-      }
-      if (threadIdx.x == 0) {
-        atomicMax(iterState + 2, (unsigned long long)done);
-        atomicAdd(iterState + 4, (unsigned long long)(S.sgStart[gEnd - 1] + S.sgCount[gEnd - 1] - S.sgStart[gBeg]) * (unsigned long long)done);
-      }
-    }
-    __syncthreads();
-  }
+// contact-iterations of the solve = sum over groups of contacts x iterations of the group's scene -> iterState[4]
+__global__ void k_row_updates(int ng, SolveArrays S, int nScenes, unsigned long long* __restrict__ iterState) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v = 0;
+  if (p < ng) v = (unsigned long long)S.sgCount[p] * (unsigned long long)S.sceneState[nScenes + S.sgScene[p]];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(iterState + 4, v);
 }
 
 // hub entries: one per (group, hub side), keyed (colour, hub body, group position) so that a radix sort groups them
 // into (colour, hub) runs with ascending group position
 __global__ void k_hub_entries(int ng, const int* __restrict__ sgFlags, const int* __restrict__ sgB1, const int* __restrict__ sgB2,
-                              const int* __restrict__ phaseOf, const int* __restrict__ scan,
+                              const int* __restrict__ phaseOf, const int* __restrict__ scan, int bitsG, int bitsB,
                               unsigned long long* __restrict__ key, int* __restrict__ slot) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= ng) return;
   int fl = sgFlags[p];
   int o = scan[p];
-  unsigned long long col = (unsigned long long)phaseOf[p];  // < 2^18 phases, bodies < 2^23, groups < 2^23 (checked on the host)
-  if (fl & SG_HUB1) { key[o] = (col << 46) | ((unsigned long long)sgB1[p] << 23) | (unsigned long long)p; slot[o] = 2 * p; o++; }
-  if (fl & SG_HUB2) { key[o] = (col << 46) | ((unsigned long long)sgB2[p] << 23) | (unsigned long long)p; slot[o] = 2 * p + 1; }
+  unsigned long long col = (unsigned long long)phaseOf[p];  // key = phase | body | group, bit widths chosen by the host (sum <= 64)
+  if (fl & SG_HUB1) { key[o] = (col << (bitsG + bitsB)) | ((unsigned long long)sgB1[p] << bitsG) | (unsigned long long)p; slot[o] = 2 * p; o++; }
+  if (fl & SG_HUB2) { key[o] = (col << (bitsG + bitsB)) | ((unsigned long long)sgB2[p] << bitsG) | (unsigned long long)p; slot[o] = 2 * p + 1; }
 }
 __global__ void k_hub_sides(int ng, const int* __restrict__ sgFlags, int* __restrict__ n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1158,32 +1097,21 @@ __global__ void k_hub_sides(int ng, const int* __restrict__ sgFlags, int* __rest
   int fl = sgFlags[p];
   n[p] = ((fl & SG_HUB1) ? 1 : 0) + ((fl & SG_HUB2) ? 1 : 0);
 }
-__global__ void k_hub_run_heads(int ne, const unsigned long long* __restrict__ key, int* __restrict__ head) {
+__global__ void k_hub_run_heads(int ne, const unsigned long long* __restrict__ key, int bitsG, int* __restrict__ head) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
-  head[e] = (e == 0 || (key[e] >> 23) != (key[e - 1] >> 23)) ? 1 : 0;
+  head[e] = (e == 0 || (key[e] >> bitsG) != (key[e - 1] >> bitsG)) ? 1 : 0;
 }
 __global__ void k_hub_run_fill(int ne, const unsigned long long* __restrict__ key, const int* __restrict__ head,
-                               const int* __restrict__ scan, const int* __restrict__ bodyLocal, const int* __restrict__ collRep, int nb,
-                               int* __restrict__ runStart, int* __restrict__ runBody, int* __restrict__ runLocal,
-                               int* __restrict__ runColor) {
+                               const int* __restrict__ scan, int bitsG, int bitsB, int* __restrict__ runStart,
+                               int* __restrict__ runBody, int* __restrict__ runColor) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne || !head[e]) return;
   int r = scan[e];
   runStart[r] = e;
-  int hb = (int)((key[e] >> 23) & 0x7fffff);
-  runLocal[r] = bodyLocal[hb < nb ? hb : collRep[hb - nb]];
+  int hb = (int)((key[e] >> bitsG) & ((1ULL << bitsB) - 1));
   runBody[r] = hb;
-  runColor[r] = (int)(key[e] >> 46);
-}
-
-__global__ void k_iter_end(unsigned long long* iterState, double tolerance, int checkTolerance) {
-  if (iterState[1]) return;
-  iterState[2] += 1;
-  double m = __longlong_as_double((long long)iterState[0]);
-  if (checkTolerance && m < tolerance) iterState[1] = 1;
-  iterState[3] = iterState[0];
-  iterState[0] = 0;
+  runColor[r] = (int)(key[e] >> (bitsG + bitsB));
 }
 
 // copy the solution back to the contact sets (set 0 = external, set 1 = internal contacts of collections) and

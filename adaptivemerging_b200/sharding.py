@@ -14,13 +14,20 @@ def shard_scenes(total_scenes, rank, world):
     return start, count
 
 
-def reduce_step_stats(ms, units, dist=None, device="cpu"):
-    """(max over ranks of the timed span in ms, sum over ranks of the units processed)."""
+def reduce_stats(maxes, sums, dist=None, device="cpu"):
+    """(element-wise MAX over ranks of `maxes` - timed spans -, element-wise SUM over ranks of `sums` - processed units)."""
+    maxes, sums = [float(x) for x in maxes], [float(x) for x in sums]
     if dist is None:
-        return float(ms), float(units)
+        return maxes, sums
     import torch
-    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
-    u = torch.tensor([float(units)], dtype=torch.float64, device=device)
+    t = torch.tensor(maxes, dtype=torch.float64, device=device)
+    u = torch.tensor(sums, dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    return float(t[0]), float(u[0])
+    return t.tolist(), u.tolist()
+
+
+def reduce_step_stats(ms, units, dist=None, device="cpu"):
+    """(max over ranks of the timed span in ms, sum over ranks of the units processed)."""
+    t, u = reduce_stats([ms], [units], dist, device)
+    return t[0], u[0]

@@ -45,12 +45,12 @@ def build_workload(name, size, merging, y0=None):
     p = default_params()
     p.enable_merging = int(merging)
     if name == "batch":
-        copies = size or 512
+        copies = size or 4096
         one = load_blob(os.path.join(GOLDEN, "scene_tower25platform.npz"))
         p = apply_overrides(p, one.overrides)
         blob = one.replicate(copies)
-        return blob, p, (f"{copies} independent copies of scenes3D/tower25platform.xml per GPU (config B of BASELINE.json: "
-                         f"4096 copies over 8 GPUs), merging {'on' if merging else 'off'}")
+        return blob, p, (f"{copies} independent copies of scenes3D/tower25platform.xml on this GPU (config B of BASELINE.json: "
+                         f"4096 copies sharded over the GPUs), merging {'on' if merging else 'off'}")
     if name in ("stack", "pile"):
         n = size or 100
         blob = box_stack(n, n, n, pile=(name == "pile"))
@@ -61,9 +61,8 @@ def build_workload(name, size, merging, y0=None):
         p = apply_overrides(p, tmpl.overrides)
         y0 = 0.6 if y0 is None else y0
         blob = funnel_pile(tmpl, nx=n, ny=10, nz=n, y0=y0)
-        return blob, p, (f"funnel.xml + {n}x10x{n} torso_flux sphere-tree bodies (config F of BASELINE.json) piled from "
-                         f"y0={y0} (SURVEY.md asks for y0=110: at dt=0.05 that impact speed tunnels the meshes into each other "
-                         f"and yields 1e4-1e5 leaf contacts per body pair, see DESIGN.md), merging {'on' if merging else 'off'}")
+        return blob, p, (f"funnel.xml + {n}x10x{n} torso_flux sphere-tree bodies (config F of BASELINE.json; full size n = 100) with the "
+                         f"lowest lattice layer at y0={y0} (SURVEY.md 8d: y0 = 110), merging {'on' if merging else 'off'}")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -141,10 +140,10 @@ def hbm_peak():
 
 def measured_traffic(kernel, workload):
     """DRAM bytes (read + write) per contact per PGS iteration of the sweep kernel, from the committed
-    `ncu --set full` capture of the same workload (profiles/r1_traffic.json; dram__bytes_read.sum +
+    `ncu --set full` capture of the same workload (profiles/r2_traffic.json; dram__bytes_read.sum +
     dram__bytes_write.sum divided by the contact-iterations of the captured launch)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             d = json.load(f)[kernel][{"pile": "stack"}.get(workload, workload)]
         return float(d["dram_bytes_per_contact_iter"]), d["source"]
     except Exception:
@@ -184,6 +183,115 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_leg(local, blob, params, steps, warmup, settle, with_e2e, barrier):
+    """One workload on this rank's GPU: settle + warm-up, K timed steps with the state resident in HBM, then (with_e2e)
+    reset, the same settle + warm-up again and the SAME K steps timed end to end through host buffers."""
+    import torch
+    from adaptivemerging_b200.system import RigidBodySystem
+    sysm = RigidBodySystem(local).load(blob, params)
+    sysm.set_option("record_events", 0)  # the merge / unmerge event log is a parity-test aid
+    for _ in range(settle + warmup):
+        sysm.advanceTime(0.05)
+    s0 = sysm.stats()
+    profiling = bool(os.environ.get("AM3D_CUDA_PROFILER"))  # ncu --profile-from-start off: capture the timed region only
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    sysm.mark(0)
+    t0 = time.perf_counter()
+    np_bytes = np_s = 0.0
+    sum_contacts = 0
+    for _ in range(steps):
+        sysm.advanceTime(0.05)
+        t = sysm.timings()
+        sum_contacts += t.n_contacts
+        # narrowphase, SURVEY.md 8d: 8 B + 2 x 96 B per candidate pair, 80 B per emitted contact
+        np_bytes += 200.0 * t.n_pairs + 80.0 * t.n_contacts
+        np_s += t.narrowphase_kernel_time
+    sysm.mark(1)
+    ms = sysm.elapsed_ms()
+    barrier()
+    wall = time.perf_counter() - t0
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
+    clk = clocks.stop()
+    s1 = sysm.stats()
+    tm = sysm.timings()
+    out = {"ms": ms, "wall": wall, "clocks": clk, "np_bytes": np_bytes, "np_s": np_s, "sum_contacts": sum_contacts,
+           "row_updates": s1["row_updates"] - s0["row_updates"], "solve_s": s1["solve_seconds"] - s0["solve_seconds"],
+           "launches": s1["kernel_launches"] - s0["kernel_launches"], "solve_launches": s1["solve_launches"] - s0["solve_launches"],
+           "tm": {"n_collections": tm.n_collections, "n_contacts": tm.n_contacts, "n_pairs": tm.n_pairs, "pgs_colors": tm.pgs_colors,
+                  "n_bodies_top_level": tm.n_bodies,
+                  "phase_ms": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "update_collections": tm.update_collections * 1e3,
+                               "contact_ordering": tm.contact_ordering * 1e3, "single_it_pgs": tm.single_it_pgs * 1e3,
+                               "unmerging": tm.unmerging * 1e3, "lcp_solve": tm.lcp_solve * 1e3, "pgs_sweeps": tm.pgs_kernel_time * 1e3,
+                               "merging": tm.merging * 1e3, "total": tm.compute_time * 1e3}},
+           "ms_e2e": None, "h2d": 0, "d2h": 0}
+    if with_e2e:
+        # ---- end-to-end leg: host buffers in, host buffers out, every step, over the SAME simulation steps ----------
+        # inputs of a step as the Java front end hands them over: per-body velocity pokes (mouse impulses / scripted
+        # pushes; zeros here) from pinned host memory; result: the full body state for drawing
+        sysm.reset()
+        sysm.set_option("record_events", 0)
+        for _ in range(settle + warmup):
+            sysm.advanceTime(0.05)
+        n = sysm.n_bodies
+        poke_v = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+        poke_w = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+        pv, pw = poke_v.numpy(), poke_w.numpy()
+        out["h2d"] = pv.nbytes + pw.nbytes
+        out["d2h"] = n * (3 + 9 + 3 + 3) * 8 + 2 * 4 * n
+
+        def pinned_state():
+            t = {"x": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "R": torch.empty((n, 9), dtype=torch.float64).pin_memory(),
+                 "v": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "omega": torch.empty((n, 3), dtype=torch.float64).pin_memory(),
+                 "sleeping": torch.empty(n, dtype=torch.int32).pin_memory(), "collection": torch.empty(n, dtype=torch.int32).pin_memory()}
+            return t, {k: a.numpy() for k, a in t.items()}
+        # two result buffers: the copy of step N's state (second stream) runs under the kernels of step N+1, as a front end
+        # that draws one frame behind would use it; every step's state is fully delivered inside the timed region
+        keep, states = zip(*(pinned_state() for _ in range(2)))
+        barrier()
+        sysm.mark(0)
+        for k in range(steps):
+            sysm.add_velocities(pv, pw)
+            sysm.advanceTime(0.05)
+            sysm.bodies_async(states[k & 1])
+        sysm.wait_bodies()
+        sysm.mark(1)
+        out["ms_e2e"] = sysm.elapsed_ms()
+        barrier()
+        out["e2e_contacts_last_step"] = sysm.timings().n_contacts
+    sysm.close()
+    return out
+
+
+def roofline_of(leg, workload, steps):
+    peak, peak_src = hbm_peak()
+    row_updates, solve_s = leg["row_updates"], leg["solve_s"]
+    achieved = (row_updates / 3.0) * PGS_BYTES_PER_CONTACT_ITER / max(solve_s, 1e-12) / 1e9
+    solve_launches = max(float(leg["solve_launches"]), 1.0)
+    persistent = solve_launches <= 2 * steps  # one cooperative launch per solve vs one launch per colour per iteration
+    kernel = "k_pgs_persistent" if persistent else "k_pgs_color<1>"
+    traffic_ratio, traffic_src = measured_traffic(kernel, workload)
+    contact_iters_per_launch = (row_updates / 3.0) / solve_launches
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None if traffic_ratio is None else traffic_ratio * contact_iters_per_launch,
+            "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes": "752 B per contact per PGS iteration (SURVEY.md 8d)",
+            "algorithmic_bytes_per_launch": PGS_BYTES_PER_CONTACT_ITER * contact_iters_per_launch,
+            "launches": int(solve_launches), "avg_launch_ms": 1e3 * solve_s / solve_launches,
+            "sweep_ms_per_step": 1e3 * solve_s / steps}
+
+
+def narrow_roofline_of(leg, steps):
+    peak, _ = hbm_peak()
+    a = leg["np_bytes"] / max(leg["np_s"], 1e-12) / 1e9
+    return {"bound": "hbm", "kernel": "k_narrow_box + k_narrow_tree<0/1>", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+            "algorithmic_bytes": "200 B per candidate pair + 80 B per contact (SURVEY.md 8d)", "ms_per_step": 1e3 * leg["np_s"] / steps}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,12 +300,17 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="batch", choices=["batch", "stack", "pile", "funnel"])
     ap.add_argument("--merging", type=int, default=1)
-    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--size", type=int, default=0, help="per-GPU size: copies (batch), edge length (stack / pile), lattice edge (funnel)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="batch only: strong = BASELINE.json's config B as written, 4096 copies in total, 4096/N per GPU; "
+                         "weak = 512 copies per GPU")
+    ap.add_argument("--y0", type=float, default=None, help="funnel: height of the lowest lattice layer (SURVEY.md: 110)")
     ap.add_argument("--settle", type=int, default=-1,
                     help="untimed steps before the warm-up so that the workload is in its loaded phase "
                          "(default: 150 batch = towers collapsing onto the platform, 20 stack/pile, 35 funnel = second layer "
                          "landing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short config M / config F legs reported under `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.settle < 0:
@@ -220,11 +333,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("no CUDA device: the rigid-body step has no CPU fallback")
 
-    from adaptivemerging_b200.system import RigidBodySystem
-    blob, params, desc = build_workload(args.workload, args.size, args.merging)
+    from adaptivemerging_b200.sharding import reduce_stats, shard_scenes
+    size = args.size
+    if args.workload == "batch" and not size:
+        # config B: 4096 independent scenes, a contiguous block of scene ids per GPU (no data-path collective)
+        size = shard_scenes(4096, rank, world)[1] if args.scaling == "strong" else 512
+    blob, params, desc = build_workload(args.workload, size, args.merging, args.y0)
     nb = int((blob.a["body_type"] != 1).sum())  # non-plane leaf bodies
-    sysm = RigidBodySystem(local).load(blob, params)
-    sysm.set_option("record_events", 0)  # the merge / unmerge event log is a parity-test aid
 
     def barrier():
         torch.cuda.synchronize()
@@ -232,76 +347,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.settle + args.warmup):
-        sysm.advanceTime(0.05)
+    leg = run_leg(local, blob, params, args.steps, args.warmup, args.settle, True, barrier)
+    del blob
 
-    # ---- resident-state leg -------------------------------------------------------------------
-    s0 = sysm.stats()
-    profiling = bool(os.environ.get("AM3D_CUDA_PROFILER"))  # ncu --profile-from-start off: capture the timed region only
-    if profiling:
-        torch.cuda.cudart().cudaProfilerStart()
-    clocks = ClockSampler(local)
-    clocks.start()
-    barrier()
-    sysm.mark(0)
-    t0 = time.perf_counter()
-    contacts = iters = 0
-    np_bytes = np_s = 0.0
-    for _ in range(args.steps):
-        sysm.advanceTime(0.05)
-        t = sysm.timings()
-        contacts += t.n_contacts
-        iters += t.pgs_iterations
-        # narrowphase, SURVEY.md 8d: 8 B + 2 x 96 B per candidate pair, 80 B per emitted contact
-        np_bytes += 200.0 * t.n_pairs + 80.0 * t.n_contacts
-        np_s += t.narrowphase_kernel_time
-    sysm.mark(1)
-    ms = sysm.elapsed_ms()
-    barrier()
-    wall = time.perf_counter() - t0
-    if profiling:
-        torch.cuda.cudart().cudaProfilerStop()
-    clk = clocks.stop()
-    s1 = sysm.stats()
-    tm = sysm.timings()
-
-    # ---- end-to-end leg: host buffers in, host buffers out, every step ------------------------------
-    # inputs of a step as the Java front end hands them over: per-body velocity pokes (mouse impulses / scripted
-    # pushes; zeros here) from pinned host memory; result: the full body state for drawing
-    n = sysm.n_bodies
-    poke_v = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
-    poke_w = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
-    pv, pw = poke_v.numpy(), poke_w.numpy()
-    h2d = pv.nbytes + pw.nbytes
-    d2h = n * (3 + 9 + 3 + 3) * 8 + 2 * 4 * n
-    def pinned_state():
-        t = {"x": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "R": torch.empty((n, 9), dtype=torch.float64).pin_memory(),
-             "v": torch.empty((n, 3), dtype=torch.float64).pin_memory(), "omega": torch.empty((n, 3), dtype=torch.float64).pin_memory(),
-             "sleeping": torch.empty(n, dtype=torch.int32).pin_memory(), "collection": torch.empty(n, dtype=torch.int32).pin_memory()}
-        return t, {k: a.numpy() for k, a in t.items()}
-    # two result buffers: the copy of step N's state (second stream) runs under the kernels of step N+1, as a front end
-    # that draws one frame behind would use it; every step's state is fully delivered inside the timed region
-    keep, states = zip(*(pinned_state() for _ in range(2)))
-    barrier()
-    sysm.mark(0)
-    for k in range(args.steps):
-        sysm.add_velocities(pv, pw)
-        sysm.advanceTime(0.05)
-        sysm.bodies_async(states[k & 1])
-    sysm.wait_bodies()
-    sysm.mark(1)
-    ms_e2e = sysm.elapsed_ms()
-    barrier()
-
-    times = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=f"cuda:{local}")
-    counts = torch.tensor([float(nb), float(s1["row_updates"] - s0["row_updates"]), float(s1["solve_seconds"] - s0["solve_seconds"]),
-                           float(s1["kernel_launches"] - s0["kernel_launches"]), float(s1["solve_launches"] - s0["solve_launches"])], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        tot = counts.clone()
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    else:
-        tot = counts
+    # MAX over ranks of the timed spans, SUM over ranks of the processed units (adaptivemerging_b200/sharding.py)
+    counts = [float(nb), float(leg["row_updates"]), float(leg["solve_s"]), float(leg["launches"])]
+    times, tot = reduce_stats([leg["ms"], leg["ms_e2e"]], counts, dist, f"cuda:{local}")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -310,47 +361,31 @@ def main():
     total_bodies = float(tot[0])
     value = total_bodies * args.steps / (ms * 1e-3)
     e2e = total_bodies * args.steps / (ms_e2e * 1e-3)
-    # roofline of the dominant kernel (rank 0's PGS sweeps)
-    row_updates = float(counts[1])
-    solve_s = float(counts[2])
-    peak, peak_src = hbm_peak()
-    achieved = (row_updates / 3.0) * PGS_BYTES_PER_CONTACT_ITER / max(solve_s, 1e-12) / 1e9
-    solve_launches = max(float(counts[4]), 1.0)
-    persistent = solve_launches <= 2 * args.steps  # one cooperative launch per solve vs one launch per colour per iteration
-    kernel = "k_pgs_persistent" if persistent else "k_pgs_color<1>"
-    traffic_ratio, traffic_src = measured_traffic(kernel, args.workload)
-    contact_iters_per_launch = (row_updates / 3.0) / solve_launches
+    tm = leg["tm"]
+    rec_mb = tm["n_contacts"] * 192.0 / 1e6
+    scaling = args.scaling if args.workload == "batch" and not args.size else "weak"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "bodies_per_gpu": nb, "dt": 0.05, "merging": bool(args.merging),
-                   "pgs_iterations": params.iterations, "settle_steps": args.settle,
-                   "l2": "working set (body + contact arrays) exceeds the 126 MB L2" if nb >= 200000 else
-                         "working set fits L2; no flush between steps (steps are data dependent)"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+        "config": {"workload": args.workload, "description": desc, "bodies_per_gpu": nb, "bodies_total": int(total_bodies), "dt": 0.05,
+                   "merging": bool(args.merging), "pgs_iterations": params.iterations, "settle_steps": args.settle,
+                   "l2": f"the PGS contact records alone are {rec_mb:.0f} MB per sweep ({'larger than' if rec_mb > 126 else 'within'} the 126 MB "
+                         "L2) and every step re-detects its contacts; no flush between steps (steps are data dependent)",
+                   "e2e_window": "the end-to-end leg repeats the resident leg's simulation steps (reset, same settle + warm-up)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": leg["h2d"], "d2h_bytes_per_step": leg["d2h"],
+                "ms_per_step": ms_e2e / args.steps, "contacts_last_step": leg.get("e2e_contacts_last_step")},
         "gpu_launches": int(float(tot[3])),
-        "clocks": clk,
-        "pgs_row_updates_per_s": float(tot[1]) / max(solve_s, 1e-12) if world == 1 else float(tot[1]) / max(solve_s, 1e-12),
+        "clocks": leg["clocks"],
+        "pgs_row_updates_per_s": float(tot[1]) / max(float(counts[2]), 1e-12),
         # BASELINE.md row "PGS contact-row updates/s": 23.4 M/s (authors' Java log, tower25platform, 30 iterations, unknown CPU);
         # body-steps/s has no published number for leaf bodies, so vs_baseline stays null
-        "pgs_row_updates_vs_baseline": (float(tot[1]) / max(solve_s, 1e-12)) / 23.4e6,
-        "collections_last_step": tm.n_collections, "contacts_last_step": tm.n_contacts, "pairs_last_step": tm.n_pairs, "pgs_colors": tm.pgs_colors,
-        "phase_ms_last_step": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "lcp_solve": tm.lcp_solve * 1e3,
-                               "pgs_sweeps": tm.pgs_kernel_time * 1e3, "post": tm.merging * 1e3, "total": tm.compute_time * 1e3},
-        "wall_ms_per_step": 1e3 * wall / args.steps,
-        "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     "traffic": None if traffic_ratio is None else traffic_ratio * contact_iters_per_launch,
-                     "traffic_source": traffic_src, "peak_source": peak_src,
-                     "algorithmic_bytes": "752 B per contact per PGS iteration (SURVEY.md 8d)",
-                     "algorithmic_bytes_per_launch": PGS_BYTES_PER_CONTACT_ITER * contact_iters_per_launch,
-                     "launches": int(solve_launches), "avg_launch_ms": 1e3 * solve_s / solve_launches},
-        "roofline_narrowphase": {"bound": "hbm", "kernel": "k_narrow_box + k_narrow_tree<0/1>", "achieved": np_bytes / max(np_s, 1e-12) / 1e9,
-                                 "peak": peak, "unit": "GB/s", "frac": np_bytes / max(np_s, 1e-12) / 1e9 / peak,
-                                 "algorithmic_bytes": "200 B per candidate pair + 80 B per contact (SURVEY.md 8d)",
-                                 "ms_per_step": 1e3 * np_s / args.steps},
+        "pgs_row_updates_vs_baseline": (float(tot[1]) / max(float(counts[2]), 1e-12)) / 23.4e6,
+        "collections_last_step": tm["n_collections"], "contacts_last_step": tm["n_contacts"], "pairs_last_step": tm["n_pairs"],
+        "pgs_phases": tm["pgs_colors"], "phase_ms_last_step": tm["phase_ms"],
+        "wall_ms_per_step": 1e3 * leg["wall"] / args.steps,
+        "roofline": roofline_of(leg, args.workload, args.steps),
+        "roofline_narrowphase": narrow_roofline_of(leg, args.steps),
     }
     if not args.no_cpu_baseline and world == 1:
         from oracle.oracle import Oracle
@@ -368,6 +403,23 @@ def main():
         line["cpu_baseline"] = {"value": snb * k / el, "unit": UNIT, "cores": 1, "kind": "port",
                                 "sample": f"{sample}, {k} steps after {args.settle} settle steps",
                                 "pgs_row_updates_per_s": o.row_updates() / max(o.solve_seconds(), 1e-12)}
+    if world == 1 and not args.no_also and args.workload == "batch" and not args.size:
+        # short legs of BASELINE.json's other single-GPU configs, so that one default run shows them all
+        also = []
+        for wl, sz, mg, st, settle, y0 in [("stack", 100, 0, 5, 20, None), ("stack", 100, 1, 5, 20, None), ("funnel", 20, 1, 3, 35, 0.6)]:
+            try:
+                b2, p2, d2 = build_workload(wl, sz, mg, y0)
+                nb2 = int((b2.a["body_type"] != 1).sum())
+                l2 = run_leg(local, b2, p2, st, 3, settle, False, barrier)
+                del b2
+                also.append({"workload": wl, "description": d2, "bodies": nb2, "merging": bool(mg), "steps": st, "settle_steps": settle,
+                             "value": nb2 * st / (l2["ms"] * 1e-3), "unit": UNIT, "ms_per_step": l2["ms"] / st,
+                             "pgs_row_updates_per_s": l2["row_updates"] / max(l2["solve_s"], 1e-12),
+                             "contacts_last_step": l2["tm"]["n_contacts"], "collections_last_step": l2["tm"]["n_collections"],
+                             "roofline": roofline_of(l2, wl, st), "roofline_narrowphase": narrow_roofline_of(l2, st)})
+            except Exception as e:  # an auxiliary leg must not take the headline line down
+                also.append({"workload": wl, "error": str(e)[:200]})
+        line["also"] = also
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
