@@ -47,7 +47,7 @@ static void fetchContacts(am3d_ctx* c, ContactSet& S, int n, am3d_contact* out, 
   gd(viol, S.viol, 1); gd(pviol, S.prevViol, 1); gd(lam, S.lam, 3); gd(lamW, S.lamWarm, 3);
   std::vector<int> gcol;
   int ng = c->nGroups;
-  if (!internal && !c->lastSolveSweep && ng > 0 && ng == c->bp.n) {
+  if (!internal && !c->lastSolveSweep && ng > 0 && ng == c->bp.n && c->nPairsSolve == ng) {
     gcol.resize(ng);
     CK(cudaMemcpyAsync(gcol.data(), c->grpColor.p, ng * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
@@ -319,8 +319,17 @@ int am3d_create(int device, am3d_ctx** out) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<false>, 128, 0)); c->coopBlocksV[0] = coop ? sms * perSm : 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pgs_persistent<true>, 128, 0));  c->coopBlocksV[1] = coop ? sms * perSm : 0;
     c->coopBlocks = c->coopBlocksV[1];
+    {
+      int gsm = GIANT_WARPS * 32 * GIANT_ROW * (int)sizeof(double);
+      CK(cudaFuncSetAttribute(k_pgs_giant<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+      CK(cudaFuncSetAttribute(k_pgs_giant<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+      CK(cudaFuncSetAttribute(k_pgs_giant<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+      CK(cudaFuncSetAttribute(k_pgs_giant<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_layers, 256, 0)); c->bfsBlocks = coop ? sms * perSm : 0;
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
+    if (const char* e = getenv("AM3D_GIANT_WARPS")) c->useGiantWarps = atoi(e);
+    if (const char* e = getenv("AM3D_GIANT_CHUNK")) c->giantChunk = atoi(e);
   } catch (const AmError& e) {
     cudaMemPool_t pool = c->pool;
     delete c;
@@ -679,7 +688,7 @@ int am3d_download_solve_order(am3d_ctx* c, int32_t* order, int capacity, int* co
   if (count) *count = n;
   if (n > capacity) throw AmError(AM3D_EINVAL, "capacity too small");
   if (n > 0) {
-    if (c->lastSolveSweep || c->nGroups != c->bp.n || c->nGroups == 0) throw AmError(AM3D_ESTATE, "no full solve has been run on the current contacts");
+    if (c->lastSolveSweep || c->nPairsSolve != c->bp.n || c->nGroups == 0) throw AmError(AM3D_ESTATE, "no full solve has been run on the current contacts");
     // order[k] = canonical contact index solved k-th
     CK(cudaMemcpyAsync(order, c->scSrc.p, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -700,6 +709,8 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   if (!strcmp(name, "hub_min_degree")) c->hubMin = (int)value;
   else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
   else if (!strcmp(name, "record_events")) c->recordEvents = value != 0;
+  else if (!strcmp(name, "giant_warps")) c->useGiantWarps = (int)value;
+  else if (!strcmp(name, "giant_chunk")) c->giantChunk = (int)value;
   else if (!strcmp(name, "merge_exact_max_pairs")) c->mergeExactMax = (int)value;
   else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);
   API_END(c)
@@ -768,6 +779,7 @@ int am3d_debug_solve_row(am3d_ctx* c, int contact, double* out /* [50] */) {
   int idx = -1;
   for (int k = 0; k < n; k++) if (src[k] == contact) idx = k;
   if (idx < 0) throw AmError(AM3D_EINVAL, "contact not in the last solve");
+  if (c->nGroups != c->nPairsSolve) throw AmError(AM3D_ESTATE, "the last solve cut body pairs into chunks: no per-pair row to show");
   auto g = [&](double* d, const double* p, int m) { CK(cudaMemcpy(d, p, m * sizeof(double), cudaMemcpyDeviceToHost)); };
   g(out, c->scP.p + 24 * (size_t)idx, 24);
   int bpc;

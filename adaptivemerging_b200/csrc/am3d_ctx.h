@@ -230,7 +230,11 @@ struct am3d_ctx {
   DevBuf<int> bodyLocal;   // rank of a leaf body among the bodies of its scene (colour priorities hash scene-local ids)
   DevBuf<int> sgScene;     // per solve group
   DevBuf<int> sceneState;  // per scene: done | moving | iterations (the tolerance exit is taken per scene)
-  DevBuf<int> phaseHead, phaseScan, sgPhase;  // (layer, colour) phases of the sorted group list
+  DevBuf<int> phaseHead, phaseScan, sgPhase, phaseGiants;
+  DevBuf<int> chN, chFirst, cgB1, cgB2, cgCount, cgStart, cgLayer, cgLead;  // body pairs cut into chunks of giantChunk contacts
+  int giantChunk = 512;   // am3d_set_option("giant_chunk", n): 0 = never split a pair
+  int nPairsSolve = 0;    // body pairs of the last solve (nGroups counts chunks)
+  int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list
   int bfsBlocks = 0;
   bool orderingTimed = false;
   std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples

@@ -16,14 +16,14 @@ static ContactPtrs contactPtrs(ContactSet& S) {
 
 // colour the groups (body pairs) so that no two groups of a colour share a non-pinned solver body
 // and order them by (layer, colour) phases; layer = nullptr for the full solve
-static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, int inCollection, const int* layer,
-                         int layerBits) {
+static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, const int* lead, int inCollection,
+                         const int* layer, int layerBits) {
   c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
   c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
   c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
   CK(cudaMemsetAsync(c->grpDegree.p, 0, c->NS * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->counters.p + 6, 0, sizeof(int), c->stream));
-  LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, gcount, c->bodyLocal.p, inCollection, c->grpSb1.p, c->grpSb2.p,
+  LAUNCH(c, k_grp_init, nblk(ng), BLK, ng, gb1, gb2, c->parent.p, c->flags.p, gcount, c->bodyLocal.p, lead, inCollection, c->grpSb1.p, c->grpSb2.p,
          c->grpPrio.p, c->grpColor.p, c->grpDegree.p);
   LAUNCH(c, k_grp_hubs, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpDegree.p, c->hubMin, c->grpHubMask.p, c->counters.p + 6);
   CK(cudaMemsetAsync(c->bodyBest.p, 0, c->NS * sizeof(unsigned long long), c->stream));
@@ -133,7 +133,28 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     layer = c->grpLayer.p;
     layerBits = 1;
   }
-  colourGroups(c, ng, gb1, gb2, gcount, sweep ? 1 : 0, layer, layerBits);
+  // cut pairs with hundreds of contacts into chunks (only scenes with sphere trees can have them)
+  const int np = ng;
+  const int *pcount = gcount, *pstart = gstart;
+  const int *chunkFirst = nullptr, *lead = nullptr;
+  int chunkLen = 0;
+  if (c->NN > 0 && c->giantChunk > 0) {
+    c->chN.ensure(np + 2); c->chFirst.ensure(np + 2);
+    LAUNCH(c, k_chunk_count, nblk(np), BLK, np, pcount, c->giantChunk, c->chN.p);
+    int total = scanTotal(c, c->chN, c->chFirst, np);
+    if (total > np) {
+      ng = total;
+      chunkLen = c->giantChunk;
+      c->cgB1.ensure(ng + 1); c->cgB2.ensure(ng + 1); c->cgCount.ensure(ng + 1); c->cgStart.ensure(ng + 1); c->cgLayer.ensure(ng + 1); c->cgLead.ensure(ng + 1);
+      LAUNCH(c, k_chunk_expand, nblk(np), BLK, np, chunkLen, c->chFirst.p, gb1, gb2, pcount, pstart, layer, c->cgB1.p, c->cgB2.p, c->cgCount.p,
+             c->cgStart.p, c->cgLayer.p, c->cgLead.p);
+      gb1 = c->cgB1.p; gb2 = c->cgB2.p; gcount = c->cgCount.p; gstart = c->cgStart.p;
+      if (layer) layer = c->cgLayer.p;
+      chunkFirst = c->chFirst.p; lead = c->cgLead.p;
+    }
+  }
+  c->nPairsSolve = np;
+  colourGroups(c, ng, gb1, gb2, gcount, lead, sweep ? 1 : 0, layer, layerBits);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
   c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1); c->sgScene.ensure(ng + 1);
   int nScenes = c->H.nscenes;
@@ -182,10 +203,22 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   for (int k = 0; k < nsets; k++) {
     ContactSet& CS = *sets[k].S;
     if (CS.n == 0) continue;
-    LAUNCH(c, k_assemble, nblk(CS.n, 128), 128, CS.n, CS.bpc.p, sets[k].groupOffset, sets[k].setId, gstart, gcount, c->grpPos.p,
+    LAUNCH(c, k_assemble, nblk(CS.n, 128), 128, CS.n, CS.bpc.p, sets[k].groupOffset, sets[k].setId, pstart, pcount, chunkFirst, chunkLen, gstart, c->grpPos.p,
            c->sgStart.p, CS.b1.p, CS.b2.p, c->parent.p, sweep ? 1 : 0, CS.pW.p, CS.nW.p, CS.t1W.p, CS.t2W.p, CS.pB1.p, CS.nB1.p,
            CS.t1B1.p, CS.t2B1.p, CS.viol.p, CS.lam.p, CS.state.p, c->x.p, c->R.p, c->v.p, c->w.p, c->force.p, c->torque.p,
            c->minv.p, c->jinv.p, c->rest.p, dt, P.feedback_stiffness, P.restitution_override, P.restitution, S);
+  }
+  // giant groups (sphere-tree pairs with hundreds of contacts) lead their phases and are solved one warp each
+  std::vector<int> giants(c->nColors, 0);
+  int nGiants = 0;
+  {
+    c->phaseGiants.ensure(c->nColors + 1);
+    CK(cudaMemsetAsync(c->phaseGiants.p, 0, (c->nColors + 1) * sizeof(int), c->stream));
+    LAUNCH(c, k_phase_giants, nblk(ng), BLK, ng, c->sgCount.p, c->sgPhase.p, c->phaseGiants.p);
+    CK(cudaMemcpyAsync(giants.data(), c->phaseGiants.p, c->nColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int g : giants) nGiants += g;
+    if (!c->useGiantWarps) { std::fill(giants.begin(), giants.end(), 0); nGiants = 0; }
   }
   // iterState: [1] every scene done, [2] largest iteration count, [4] contact-iterations, [6] scenes still iterating
   unsigned long long is0[8] = {0, 0, 0, 0, 0, 0, (unsigned long long)nScenes, 0};
@@ -197,7 +230,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   // many small colours (hubs, batched scenes): one cooperative launch with grid barriers; few large colours: one
   // launch per colour (no barrier cost, full occupancy per launch)
   long long avgGroups = ng / std::max(1, c->nColors);
-  bool persistent = c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
+  bool persistent = nGiants == 0 && c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
   if (persistent) {
     int nColors = c->nColors;
     const int* dcs = c->dColorStart.p;
@@ -216,9 +249,25 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     c->kernelLaunches++;
     if (!sweep) c->solveLaunches++;
   } else {
+    const bool hubs = c->nHubRuns > 0;
+    const size_t gsm = (size_t)GIANT_WARPS * 32 * GIANT_ROW * sizeof(double);
+    auto giantLaunch = [&](int mode, int g0, int n, int last) {
+      int grid = (n + GIANT_WARPS - 1) / GIANT_WARPS;
+      if (mode == 0) {
+        if (hubs) k_pgs_giant<0, true><<<grid, 32 * GIANT_WARPS, gsm, c->stream>>>(g0, g0 + n, S, c->dv.p, PP, last, c->iterState.p);
+        else k_pgs_giant<0, false><<<grid, 32 * GIANT_WARPS, gsm, c->stream>>>(g0, g0 + n, S, c->dv.p, PP, last, c->iterState.p);
+      } else {
+        if (hubs) k_pgs_giant<1, true><<<grid, 32 * GIANT_WARPS, gsm, c->stream>>>(g0, g0 + n, S, c->dv.p, PP, last, c->iterState.p);
+        else k_pgs_giant<1, false><<<grid, 32 * GIANT_WARPS, gsm, c->stream>>>(g0, g0 + n, S, c->dv.p, PP, last, c->iterState.p);
+      }
+      CK(cudaGetLastError());
+      c->kernelLaunches++;
+    };
     for (int k = 0; k < c->nColors; k++) {
       int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-      LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+      if (giants[k] > 0) { giantLaunch(0, g0, giants[k], 0); g0 += giants[k]; }
+      if (hubs) LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+      else LAUNCH(c, (k_pgs_color<0, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
       int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
       if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 0, 0);
     }
@@ -226,7 +275,8 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
       int last = it == iterations - 1;
       for (int k = 0; k < c->nColors; k++) {
         int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-        if (c->nHubRuns > 0) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        if (giants[k] > 0) { giantLaunch(1, g0, giants[k], last); g0 += giants[k]; }
+        if (hubs) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         else LAUNCH(c, (k_pgs_color<1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
         int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
         if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 1, PP.check);

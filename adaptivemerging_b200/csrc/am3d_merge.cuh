@@ -819,6 +819,32 @@ __global__ void k_bfs_finalize(int ng, int nExt, const int* __restrict__ gasleep
     if (gasleep[g]) gcount[g] = 0;
   }
 }
+// A body pair with hundreds of contacts (sphere trees) is cut into CHUNKS of at most `ch` consecutive contacts, and the
+// chunks - not the pair - are what gets coloured and scheduled: the chunks of one pair share both bodies, so they land
+// in different phases, but the pairs of OTHER bodies interleave with them.  The sweep then costs about the largest
+// per-body contact load instead of (number of giant-holding colours) x (longest pair).  Any interleaving is a
+// Gauss-Seidel sequence; the oracle replays the one chosen here.
+__global__ void k_chunk_count(int np, const int* __restrict__ pcount, int ch, int* __restrict__ n) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < np) n[g] = pcount[g] > ch ? (pcount[g] + ch - 1) / ch : 1;
+}
+__global__ void k_chunk_expand(int np, int ch, const int* __restrict__ first, const int* __restrict__ pb1, const int* __restrict__ pb2,
+                               const int* __restrict__ pcount, const int* __restrict__ pstart, const int* __restrict__ player,
+                               int* __restrict__ gb1, int* __restrict__ gb2, int* __restrict__ gcount, int* __restrict__ gstart,
+                               int* __restrict__ glayer, int* __restrict__ glead) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= np) return;
+  int e0 = first[g], e1 = first[g + 1];
+  int cnt = pcount[g], st = pstart[g];
+  for (int e = e0; e < e1; e++) {
+    int off = (e - e0) * ch;
+    gb1[e] = pb1[g]; gb2[e] = pb2[g];
+    gstart[e] = st + off;
+    gcount[e] = (e1 - e0 == 1) ? cnt : min(ch, cnt - off);
+    if (player) glayer[e] = player[g];
+    glead[e] = e == e0;
+  }
+}
 // organize_contacts = false: external pairs first, then the internal pairs of awake collections
 __global__ void k_plain_layers(int ng, int nExt, const int* __restrict__ gasleep, int* __restrict__ grpLayer, int* __restrict__ gcount) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;

@@ -492,7 +492,8 @@ __device__ __forceinline__ unsigned int hash32(unsigned int a) {
 }
 // solver bodies of a group: parent collection unless computeInCollection; negative (-1 - body) for a pinned body
 __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ parent,
-                           const int* __restrict__ flags, const int* __restrict__ gcount, const int* __restrict__ bodyLocal, int inCollection,
+                           const int* __restrict__ flags, const int* __restrict__ gcount, const int* __restrict__ bodyLocal,
+                           const int* __restrict__ lead /* chunked pairs: 1 on the first chunk of a pair; or nullptr */, int inCollection,
                            int* __restrict__ sb1, int* __restrict__ sb2, unsigned long long* __restrict__ prio,
                            int* __restrict__ color, int* __restrict__ degree) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,8 +509,10 @@ __global__ void k_grp_init(int ng, const int* __restrict__ gb1, const int* __res
   bool pa = (flags[a] & AM3D_F_PINNED) || cnt == 0, pb = (flags[b] & AM3D_F_PINNED) || cnt == 0;
   sb1[g] = pa ? -1 - a : a;
   sb2[g] = pb ? -1 - b : b;
-  if (!pa) atomicAdd(degree + a, 1);
-  if (!pb) atomicAdd(degree + b, 1);
+  if (!lead || lead[g]) {  // degree in body pairs (decides what is a hub), not in chunks
+    if (!pa) atomicAdd(degree + a, 1);
+    if (!pb) atomicAdd(degree + b, 1);
+  }
   // Jones-Plassmann priority: hashed, except that long groups (sphere-tree pairs with hundreds of contacts, solved
   // as one sequential chain) come first by size class: giants that do not touch each other then share the first
   // colours, and a sweep costs the longest chain per colour instead of one giant per colour
@@ -665,8 +668,9 @@ __global__ void k_group_setup(int ng, const int* __restrict__ order /* solve pos
 // output in solve order.  Body state is read through the solver-body index (collection parent unless
 // inCollection).
 __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset, int setId,
-                           const int* __restrict__ gstart /* group -> first contact in its set */,
-                           const int* __restrict__ gcount, const int* __restrict__ grpPos,
+                           const int* __restrict__ gstart /* body pair -> first contact in its set */,
+                           const int* __restrict__ gcount, const int* __restrict__ chunkFirst /* pair -> first chunk, or nullptr */,
+                           int chunkLen, const int* __restrict__ chunkStart, const int* __restrict__ grpPos,
                            const int* __restrict__ sgStart, const int* __restrict__ cb1,
                            const int* __restrict__ cb2, const int* __restrict__ parent, int inCollection,
                            const double* __restrict__ pW, const double* __restrict__ nW, const double* __restrict__ t1W,
@@ -683,7 +687,13 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
   if (g < 0) return;
   g += groupOffset;
   if (gcount[g] == 0) return;  // internal pair of a sleeping collection: not part of the sweep
-  int idx = sgStart[grpPos[g]] + (i - gstart[g]);
+  int idx;
+  if (chunkFirst) {
+    int e = chunkFirst[g] + (chunkFirst[g + 1] - chunkFirst[g] > 1 ? (i - gstart[g]) / chunkLen : 0);
+    idx = sgStart[grpPos[e]] + (i - chunkStart[e]);
+  } else {
+    idx = sgStart[grpPos[g]] + (i - gstart[g]);
+  }
   int l1 = cb1[i], l2 = cb2[i];
   int a = l1, b = l2;
   bool touchesCollection = parent[l1] >= 0 || parent[l2] >= 0;
@@ -974,6 +984,193 @@ __device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __r
     sceneState[s] = 1;
     if (atomicAdd(iterState + 6, (unsigned long long)-1LL) == 1ULL) iterState[1] = 1;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GIANT groups (two sphere-tree meshes pressed together: 10^3 - 10^4 leaf x leaf contacts in ONE body pair,
+// CollisionProcessor.java:975-1056).  Their contacts share both bodies, so Gauss-Seidel prescribes one long chain; what
+// can be taken off the chain is everything that does not depend on deltaV.  One WARP per giant group:
+//   * prepare: the 32 lanes load 32 consecutive contact records (coalesced) and each lane works out, for its contact,
+//     the angular Jacobian halves (d x r1, r2 x d), jinv * (angular half) for both bodies, D + compliance and its
+//     reciprocal - the same operations in the same order as the one-thread form, so the results are bit-identical -
+//     and parks them in shared memory (60 doubles per contact);
+//   * chain: all lanes then walk the 32 contacts in sequence with uniform (broadcast) shared-memory reads: per row
+//     only J*deltaV, the lambda update and the two deltaV updates remain (~85 instead of ~200 instructions, no
+//     global-memory latency on the chain); lane c keeps contact c's new lambda / state and writes them back coalesced.
+// ------------------------------------------------------------------------------------------------
+#define GIANT_MIN 65       // contacts from which a group is solved by a warp
+#define GIANT_ROW 60       // doubles per prepared contact
+#define GIANT_WARPS 4      // warps per CTA of k_pgs_giant
+template <int MODE, bool HUB>
+__global__ void __launch_bounds__(32 * GIANT_WARPS)
+k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
+            unsigned long long* __restrict__ iterState) {
+  extern __shared__ __align__(16) double giantSm[];  // [GIANT_WARPS][32][GIANT_ROW]
+  if (MODE == 1 && iterState[1]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = gBegin + blockIdx.x * GIANT_WARPS + warp;
+  if (p >= gEnd) return;
+  int scene = 0;
+  if (MODE == 1 && P.check) {
+    scene = S.sgScene[p];
+    if (S.sceneState[scene]) return;
+  }
+  double* W = giantSm + (size_t)warp * 32 * GIANT_ROW;
+  const int a = S.sgB1[p], b = S.sgB2[p];
+  const int start = S.sgStart[p], cnt = S.sgCount[p];
+  double M[20];
+  const double* Mp = S.sgMass + 20 * (size_t)p;
+#pragma unroll
+  for (int k = 0; k < 5; k++) ld4(Mp + 4 * k, M + 4 * k);
+  const double mu = S.sgMu[p];
+  const int fl = S.sgFlags[p];
+  const bool clamp = fl & SG_CLAMP;
+  const bool hubA = HUB && (fl & SG_HUB1), hubB = HUB && (fl & SG_HUB2);
+  double dv1[8], dv2[8], acc1[6], acc2[6];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
+  if (a >= 0) { ld4cg(dv + DVS * (size_t)a, dv1); ld4cg(dv + DVS * (size_t)a + 4, dv1 + 4); }
+  if (b >= 0) { ld4cg(dv + DVS * (size_t)b, dv2); ld4cg(dv + DVS * (size_t)b + 4, dv2 + 4); }
+#pragma unroll
+  for (int k = 0; k < 6; k++) { acc1[k] = 0.0; acc2[k] = 0.0; }
+  double localMax = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int n = min(32, cnt - base);
+    double* PK = S.scP + 24 * (size_t)(start + base + lane);
+    // ---- prepare: lane i -> contact base + i ----
+    if (lane < n) {
+      double Q[24];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ld4(PK + 4 * k, Q + 4 * k);
+      double* R = W + lane * GIANT_ROW;
+      d3 r1 = {Q[9], Q[10], Q[11]}, r2 = {Q[12], Q[13], Q[14]};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        d3 dir = {Q[3 * k], Q[3 * k + 1], Q[3 * k + 2]};
+        d3 jaw = vcross(dir, r1), jbw = vcross(r2, dir);
+        R[3 * k] = dir.x; R[3 * k + 1] = dir.y; R[3 * k + 2] = dir.z;
+        R[9 + 3 * k] = jaw.x; R[10 + 3 * k] = jaw.y; R[11 + 3 * k] = jaw.z;
+        R[18 + 3 * k] = jbw.x; R[19 + 3 * k] = jbw.y; R[20 + 3 * k] = jbw.z;
+        const double* J1 = M + 1;
+        const double* J2 = M + 11;
+        R[27 + 3 * k] = J1[0] * jaw.x + J1[1] * jaw.y + J1[2] * jaw.z;
+        R[28 + 3 * k] = J1[3] * jaw.x + J1[4] * jaw.y + J1[5] * jaw.z;
+        R[29 + 3 * k] = J1[6] * jaw.x + J1[7] * jaw.y + J1[8] * jaw.z;
+        R[36 + 3 * k] = J2[0] * jbw.x + J2[1] * jbw.y + J2[2] * jbw.z;
+        R[37 + 3 * k] = J2[3] * jbw.x + J2[4] * jbw.y + J2[5] * jbw.z;
+        R[38 + 3 * k] = J2[6] * jbw.x + J2[7] * jbw.y + J2[8] * jbw.z;
+        R[45 + k] = Q[15 + k];                      // b
+        R[48 + k] = Q[18 + k];                      // D
+        double den = Q[18 + k] + P.compliance;
+        R[51 + k] = den;
+        R[54 + k] = 1.0 / den;
+        R[57 + k] = Q[21 + k];                      // lambda
+      }
+    }
+    __syncwarp();
+    // ---- chain: every lane runs it (uniform), lane c keeps contact c's results ----
+    double myLam[3] = {0, 0, 0}, myD2 = 0;
+    int mySt = 0;
+    for (int c = 0; c < n; c++) {
+      const double* R = W + c * GIANT_ROW;
+      double lam[3] = {R[57], R[58], R[59]};
+      double w12[2] = {0, 0};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
+        d3 jav = vscale(-1, dir);
+        d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
+        d3 ta = {R[27 + 3 * k], R[28 + 3 * k], R[29 + 3 * k]}, tb = {R[36 + 3 * k], R[37 + 3 * k], R[38 + 3 * k]};
+        double diff;
+        if (MODE == 0) diff = lam[k];
+        else {
+          double Jdv = dot6(jav, jaw, dv1) + dot6(dir, jbw, dv2);
+          double prev = lam[k];
+          double l = divExact(R[48 + k] * prev - P.omega * (R[45 + k] + Jdv), R[51 + k], R[54 + k]);
+          if (clamp) {
+            if (k == 0) l = fmax(0.0, l);
+            else {
+              double limit = mu * lam[0];
+              l = fmax(l, -limit);
+              l = fmin(l, limit);
+            }
+          }
+          lam[k] = l;
+          diff = l - prev;
+          localMax = fmax(localMax, fabs(diff));
+        }
+        // PGS.updateDeltaVwithLambdai :221-245 with jinv * (angular half) taken from the prepared row
+        if (a >= 0) {
+          double s1 = M[0] * diff;
+          dv1[0] = s1 * jav.x + dv1[0]; dv1[1] = s1 * jav.y + dv1[1]; dv1[2] = s1 * jav.z + dv1[2];
+          dv1[3] = diff * ta.x + dv1[3]; dv1[4] = diff * ta.y + dv1[4]; dv1[5] = diff * ta.z + dv1[5];
+          if (hubA) {
+            acc1[0] = s1 * jav.x + acc1[0]; acc1[1] = s1 * jav.y + acc1[1]; acc1[2] = s1 * jav.z + acc1[2];
+            acc1[3] = diff * ta.x + acc1[3]; acc1[4] = diff * ta.y + acc1[4]; acc1[5] = diff * ta.z + acc1[5];
+          }
+        }
+        if (b >= 0) {
+          double s2 = M[10] * diff;
+          dv2[0] = s2 * dir.x + dv2[0]; dv2[1] = s2 * dir.y + dv2[1]; dv2[2] = s2 * dir.z + dv2[2];
+          dv2[3] = diff * tb.x + dv2[3]; dv2[4] = diff * tb.y + dv2[4]; dv2[5] = diff * tb.z + dv2[5];
+          if (hubB) {
+            acc2[0] = s2 * dir.x + acc2[0]; acc2[1] = s2 * dir.y + acc2[1]; acc2[2] = s2 * dir.z + acc2[2];
+            acc2[3] = diff * tb.x + acc2[3]; acc2[4] = diff * tb.y + acc2[4]; acc2[5] = diff * tb.z + acc2[5];
+          }
+        }
+      }
+      if (MODE == 1) {
+        int st = 0;
+        if (lastIter) {  // Contact.updateContactState :385-398, with the deltaV after this contact's three rows
+#pragma unroll
+          for (int k = 1; k < 3; k++) {
+            d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
+            d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
+            w12[k - 1] = R[45 + k] + (dot6(vscale(-1, dir), jaw, dv1) + dot6(dir, jbw, dv2));
+          }
+          if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
+          else if (fabs(w12[0]) > P.sliding) st = AM3D_CS_ONEDGE;
+          else if (fabs(w12[1]) > P.sliding) st = AM3D_CS_ONEDGE;
+          else st = AM3D_CS_CLEAR;
+        }
+        if (lane == c) { myLam[0] = lam[0]; myLam[1] = lam[1]; myLam[2] = lam[2]; myD2 = R[50]; mySt = st; }
+      }
+    }
+    if (MODE == 1 && lane < n) {
+      st4(PK + 20, myD2, myLam[0], myLam[1], myLam[2]);
+      if (lastIter) S.scState[start + base + lane] = mySt;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    if (a >= 0) {
+      if (!hubA) {
+        st4(dv + DVS * (size_t)a, dv1[0], dv1[1], dv1[2], dv1[3]);
+        st4(dv + DVS * (size_t)a + 4, dv1[4], dv1[5], 0.0, 0.0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + k] = acc1[k];
+      }
+    }
+    if (b >= 0) {
+      if (!hubB) {
+        st4(dv + DVS * (size_t)b, dv2[0], dv2[1], dv2[2], dv2[3]);
+        st4(dv + DVS * (size_t)b + 4, dv2[4], dv2[5], 0.0, 0.0);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) S.hubDelta[12 * (size_t)p + 6 + k] = acc2[k];
+      }
+    }
+    if (MODE == 1 && P.check && !(localMax < P.tolerance)) {
+      int* f = S.sceneState + 2 * P.nScenes + (size_t)scene * MV_SLOTS + (blockIdx.x & (MV_SLOTS - 1));
+      if (!__ldcg(f)) *f = 1;
+    }
+  }
+}
+// giant groups per phase (they lead their phase: groups are sorted by descending contact count)
+__global__ void k_phase_giants(int ng, const int* __restrict__ sgCount, const int* __restrict__ phaseOf, int* __restrict__ phaseGiants) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < ng && sgCount[p] >= GIANT_MIN) atomicAdd(phaseGiants + phaseOf[p], 1);
 }
 
 // Fold the per-group deltas of one colour into the hubs' deltaV: one warp per (colour, hub) run, lanes take the
