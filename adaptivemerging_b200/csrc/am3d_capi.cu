@@ -8,12 +8,17 @@
 // ------------------------------------------------------------------------------------------------
 // the step
 // ------------------------------------------------------------------------------------------------
-static void applyExternalForces(am3d_ctx* c) {
+static void applyCoriolis(am3d_ctx* c, double dt, int topOnly) {
+  if (c->P.use_coriolis)
+    LAUNCH(c, k_coriolis, nblk(c->NS), BLK, c->NS, c->NB, c->collAlive.p, c->parent.p, c->flags.p, c->w.p, c->jinv.p, c->mA.p, c->torque.p, dt, topOnly);
+}
+static void applyExternalForces(am3d_ctx* c, double dt) {
   const am3d_params& P = c->P;
   double theta = P.gravity_angle_deg / 180.0 * M_PI;
   double gx = P.gravity_amount * cos(theta), gy = P.gravity_amount * sin(theta);
   LAUNCH(c, k_clear_gravity, nblk(c->NS), BLK, c->NS, c->NB, c->collAlive.p, c->parent.p, c->mass.p, c->x.p, c->v.p, c->w.p,
          c->force.p, c->torque.p, c->dv.p, P.use_gravity, gx, gy);
+  applyCoriolis(c, dt, 0);
   if (P.springs_enabled && c->nSpringBodies > 0)
     LAUNCH(c, k_springs, nblk(c->nSpringBodies, 64), 64, c->nSpringBodies, c->spBodies.p, c->spBodyStart.p, c->spBodyList.p,
            c->spType.p, c->spB1.p, c->spB2.p, c->spPb1.p, c->spPb2.p, c->spPw.p, c->spK.p, c->spD.p, c->spL0.p, c->spLs.p,
@@ -71,15 +76,15 @@ static void fetchContacts(am3d_ctx* c, ContactSet& S, int n, am3d_contact* out, 
 
 // tests: turn the recorded solve sequence into contact identities while the tables it indexes are still intact
 static void snapshotOrder(am3d_ctx* c, int which) {
-  std::vector<int>& ord = which ? c->orderSweep : c->orderFull;
-  std::vector<am3d_contact>& dst = which ? c->orderSweepKeys : c->orderFullKeys;
+  std::vector<int>& ord = which == 1 ? c->orderSweep : which == 2 ? c->orderPost : c->orderFull;
+  std::vector<am3d_contact>& dst = which == 1 ? c->orderSweepKeys : which == 2 ? c->orderPostKeys : c->orderFullKeys;
   dst.clear();
   CK(cudaStreamSynchronize(c->stream));
   int n = (int)ord.size();
   if (n == 0) return;
-  std::vector<am3d_contact> ext(c->cur.n), in(which ? c->icon.n : 0);
+  std::vector<am3d_contact> ext(c->cur.n), in(which == 1 ? c->icon.n : 0);
   fetchContacts(c, c->cur, c->cur.n, ext.data(), 0);
-  if (which) fetchContacts(c, c->icon, c->icon.n, in.data(), 1);
+  if (which == 1) fetchContacts(c, c->icon, c->icon.n, in.data(), 1);
   // per solve position: dense colour index and hub sides of the group the contact belongs to
   int ng = c->nGroups;
   std::vector<int> sgStart(ng), sgCount(ng), sgFlags(ng), sgPhase(ng);
@@ -119,6 +124,50 @@ static void sortBpPrev(am3d_ctx* c) {
   c->bpPrev.n = n;
 }
 
+// surviving external body pairs become the lookup table of the next detection (histories carry over)
+static void carryBodyPairs(am3d_ctx* c) {
+  int nbp = c->bp.n, nAlive = 0;
+  if (nbp > 0) {
+    c->tmpI1.ensure(nbp + 2);
+    nAlive = scanTotal(c, c->bp.alive, c->tmpI1, nbp);
+    c->bpPrev.ensure(nAlive + 1);
+    LAUNCH(c, k_bpc_compact, nblk(nbp), BLK, nbp, c->bp.alive.p, c->tmpI1.p, c->bp.key.p, c->bp.b1.p, c->bp.b2.p, c->bp.metricHist.p,
+           c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p,
+           c->bpPrev.metricHist.p, c->bpPrev.stateHist.p, c->bpPrev.nMetric.p, c->bpPrev.nState.p);
+  }
+  c->bpPrev.n = nAlive;
+  if (c->bpTail) sortBpPrev(c);
+}
+
+// RigidBodySystem.postStabilization (:354-377): detect again at the advanced positions, solve the position-level problem
+// (right-hand side = feedbackStiffness * violation, PGS.java:86-89) and move the bodies by the resulting deltaV
+static void postStabilization(am3d_ctx* c, double dt) {
+  int NS = c->NS, NB = c->NB;
+  carryBodyPairs(c);  // the BodyPairContact objects (with this step's histories) are what the second detection refills
+  if (c->nCollections > 0)  // RigidCollection.clearBodies :100-105: members take the collection's velocity at their new positions
+    LAUNCH(c, k_members_take_velocity, nblk(NB), BLK, NB, c->parent.p, c->x.p, c->v.p, c->w.p);
+  CK(cudaMemsetAsync(c->force.p, 0, 3 * (size_t)NS * sizeof(double), c->stream));   // RigidBody.clear :276-280
+  CK(cudaMemsetAsync(c->torque.p, 0, 3 * (size_t)NS * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(c->dv.p, 0, DVS * (size_t)NS * sizeof(double), c->stream));
+  detect(c);
+  buildBodyPairs(c);
+  warmStart(c, true);
+  runSolve(c, dt, false, true);
+  c->orderPostKeys.clear();
+  if (c->recordOrders) snapshotOrder(c, 2);
+  int nbp = c->bp.n;
+  if (nbp > 0) {
+    if (c->cur.n == 0) CK(cudaMemsetAsync(c->bp.nActive.p, 0, nbp * sizeof(int), c->stream));
+    LAUNCH(c, k_bpc_prune, nblk(nbp), BLK, nbp, c->bp.nActive.p, c->bp.alive.p);  // clearBodyPairContacts :374
+  }
+  // advancePositionsPostStabilization (RigidBody.java:423-425): advancePositions with (deltaV.v, deltaV.w)
+  LAUNCH(c, k_advance_positions, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->flags.p, c->x.p, c->R.p, c->dv.p, c->dv.p + 3, DVS,
+         c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p, dt);
+  if (c->nCollections > 0)
+    LAUNCH(c, k_members_follow, nblk(NB), BLK, NB, c->parent.p, c->flags.p, 0, 1, c->x.p, c->R.p, c->v.p, c->w.p, c->B2CR.p, c->B2Ct.p,
+           c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p);
+}
+
 static void stepOnce(am3d_ctx* c, double dt) {
   const am3d_params& P = c->P;
   int NS = c->NS, NB = c->NB;
@@ -126,7 +175,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
   double theta = P.gravity_angle_deg / 180.0 * M_PI;
   double gx = P.gravity_amount * cos(theta), gy = P.gravity_amount * sin(theta);
   CK(cudaEventRecord(c->ev[0], c->stream));
-  applyExternalForces(c);                       // clearBodies + applyExternalForces  (:108-116)
+  applyExternalForces(c, dt);                   // clearBodies + applyExternalForces  (:108-116)
   CK(cudaEventRecord(c->ev[1], c->stream));
   detect(c);                                    // updateContactsMap + collisionDetection (:119-120)
   buildBodyPairs(c);                            // updateBodyPairContacts (:121)
@@ -155,6 +204,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
   if (c->mergingEvent) {                        // sticky flag (:138-142): clear + re-apply forces on top-level bodies
     LAUNCH(c, k_reclear_top, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->mass.p, c->force.p, c->torque.p, c->dv.p,
            P.use_gravity, gx, gy);
+    applyCoriolis(c, dt, 0);  // applyExternalForces runs again in full: second gyroscopic term, Coriolis torque on members too
     applySprings(c);
   }
   CK(cudaEventRecord(c->ev[4], c->stream));
@@ -181,27 +231,18 @@ static void stepOnce(am3d_ctx* c, double dt) {
            c->hasExt.p);                                                                         // (:158)
   }
   LAUNCH(c, k_advance_positions, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->flags.p, c->x.p, c->R.p, c->v.p,
-         c->w.p, c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p, dt);                                   // (:160)
+         c->w.p, 3, c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p, dt);                                // (:160)
   if (c->nCollections > 0)
     LAUNCH(c, k_members_follow, nblk(NB), BLK, NB, c->parent.p, c->flags.p, 0, 1, c->x.p, c->R.p, c->v.p, c->w.p, c->B2CR.p, c->B2Ct.p,
            c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p);
+  c->orderPostKeys.clear();
+  if (P.enable_post_stabilization) { postStabilization(c, dt); nbp = c->bp.n; }                  // (:162-163)
   CK(cudaEventRecord(c->ev[6], c->stream));
   if ((c->totalSteps % P.steps_between_merge) == 0) mergeStep(c);                                // (:166-167)
   CK(cudaEventRecord(c->ev[15], c->stream));
   if (nbp > 0)
     LAUNCH(c, k_has_ext, nblk(nbp), BLK, nbp, c->bp.alive.p, c->bp.b1.p, c->bp.b2.p, c->parent.p, c->flags.p, c->hasExt.p);
-  // surviving external body pairs become next step's lookup table
-  int nAlive = 0;
-  if (nbp > 0) {
-    c->tmpI1.ensure(nbp + 2);
-    nAlive = scanTotal(c, c->bp.alive, c->tmpI1, nbp);
-    c->bpPrev.ensure(nAlive + 1);
-    LAUNCH(c, k_bpc_compact, nblk(nbp), BLK, nbp, c->bp.alive.p, c->tmpI1.p, c->bp.key.p, c->bp.b1.p, c->bp.b2.p, c->bp.metricHist.p,
-           c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p,
-           c->bpPrev.metricHist.p, c->bpPrev.stateHist.p, c->bpPrev.nMetric.p, c->bpPrev.nState.p);
-  }
-  c->bpPrev.n = nAlive;
-  if (c->bpTail) sortBpPrev(c);
+  carryBodyPairs(c);
   if (P.enable_sleeping)                                                                         // (:170)
     LAUNCH(c, k_sleep, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->flags.p, c->hasExt.p, c->metricHist.p,
            c->metricCount.p, c->x.p, c->R.p, c->v.p, c->w.p, c->bbB.p, c->bbCount.p, P.sleep_step_accum, P.sleep_threshold);
@@ -256,9 +297,7 @@ static void waitPending(am3d_ctx* c) {
 
 static void checkParams(const am3d_params* p) {
   if (p->shuffle) throw AmError(AM3D_EUNSUPPORTED, "shuffle is not supported");
-  if (p->enable_post_stabilization) throw AmError(AM3D_EUNSUPPORTED, "post-stabilisation is not supported");
   if (p->collection_cd != 0) throw AmError(AM3D_EUNSUPPORTED, "only the brute-force collection collision mode is supported");
-  if (p->use_coriolis) throw AmError(AM3D_EUNSUPPORTED, "Coriolis term is not supported");
   if (p->merge_cycle_condition) throw AmError(AM3D_EUNSUPPORTED, "cycle merge condition is not supported");
   if (p->metric_position_level) throw AmError(AM3D_EUNSUPPORTED, "position-level metric is not supported");
   if (p->iterations < 1 || p->iterations_in_collection < 1) throw AmError(AM3D_EINVAL, "iterations must be >= 1");
@@ -587,9 +626,10 @@ int am3d_record_orders(am3d_ctx* c, int on) {
 // which = 0: last full solve, 1: last single sweep.  Only the identity fields of `out` are filled.
 int am3d_download_order(am3d_ctx* c, int which, am3d_contact* out, int capacity, int* count) {
   API_BEGIN(c)
-  std::vector<am3d_contact>& keys = which ? c->orderSweepKeys : c->orderFullKeys;
+  std::vector<am3d_contact>& keys = which == 1 ? c->orderSweepKeys : which == 2 ? c->orderPostKeys : c->orderFullKeys;
   int n = (int)keys.size();
   if (count) *count = n;
+  if (!out) return AM3D_OK;  // size query
   if (n > capacity) throw AmError(AM3D_EINVAL, "capacity too small");
   if (n) memcpy(out, keys.data(), (size_t)n * sizeof(am3d_contact));
   API_END(c)
@@ -660,7 +700,7 @@ int am3d_detect(am3d_ctx* c) {
 int am3d_solve(am3d_ctx* c, double dt) {
   API_BEGIN(c)
   if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
-  applyExternalForces(c);  // clear + gravity + springs, deltaV = 0
+  applyExternalForces(c, dt);  // clear + gravity + springs, deltaV = 0
   runSolve(c, dt, false);
   c->orderFullKeys.clear();
   if (c->recordOrders) snapshotOrder(c, 0);

@@ -204,6 +204,7 @@ struct am3d_ctx {
 
   ContactSet cur, prev;
   BpcSet bp, bpPrev, bpTmp;
+  int bpSlot = 0;       // which of counters[8..9] holds this detection's largest pair
   bool bpTail = false;  // bp holds pairs appended by an unmerge (not in key order)
 
   // ---- merging ------------------------------------------------------------------------------------
@@ -240,8 +241,8 @@ struct am3d_ctx {
   std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples
   bool recordEvents = true; // am3d_set_option("record_events", 0): long batched runs (one device->host copy per merge step saved)
   bool recordOrders = false;
-  std::vector<int> orderFull, orderSweep;
-  std::vector<am3d_contact> orderFullKeys, orderSweepKeys;
+  std::vector<int> orderFull, orderSweep, orderPost;
+  std::vector<am3d_contact> orderFullKeys, orderSweepKeys, orderPostKeys;
   bool lastSolveSweep = false;
   int lastSolveN = 0;
 

@@ -105,16 +105,18 @@ static void buildBodyPairs(am3d_ctx* c) {
     c->bp.ensure(nbp + 1);
     LAUNCH(c, k_bpc_fill, nblk(nc), BLK, nc, c->cur.key0.p, c->tmpI0.p, c->tmpI1.p, c->cur.b1.p, c->cur.b2.p, c->flags.p,
            c->cur.bpc.p, c->bp.key.p, c->bp.start.p, c->bp.b1.p, c->bp.b2.p);
-    CK(cudaMemsetAsync(c->counters.p + 8 + (c->totalSteps & 1), 0, sizeof(int), c->stream));
+    c->bpSlot ^= 1;  // [8 + slot]: largest contact count of a pair in THIS detection, [8 + (slot ^ 1)]: in the one before
+    CK(cudaMemsetAsync(c->counters.p + 8 + c->bpSlot, 0, sizeof(int), c->stream));
     LAUNCH(c, k_bpc_match, nblk(nbp), BLK, nbp, nc, c->bp.key.p, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p,
            c->bp.nActive.p, c->bp.metricHist.p, c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, c->bp.alive.p,
            c->bpPrev.n, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p, c->bpPrev.metricHist.p, c->bpPrev.stateHist.p,
-           c->bpPrev.nMetric.p, c->bpPrev.nState.p, c->counters.p + 8 + (c->totalSteps & 1));
+           c->bpPrev.nMetric.p, c->bpPrev.nState.p, c->counters.p + 8 + c->bpSlot);
   }
   c->bp.n = nbp;
 }
 
-static void warmStart(am3d_ctx* c) {
+// postStab: warmStart(true) of postStabilization keeps the violation the donor itself inherited (CollisionProcessor.java:569-572)
+static void warmStart(am3d_ctx* c, bool postStab = false) {
   int nbp = c->bp.n;
   if (nbp == 0) return;
   int nt = c->prev.n - c->prev.nSorted;
@@ -127,7 +129,7 @@ static void warmStart(am3d_ctx* c) {
   }
   int ns = c->prev.nSorted;
   // a pair of sphere trees can hold 10^4+ contacts: index last step's contacts when it had such pairs
-  int useIdx = c->NN > 0 && ns > 0 && readInt(c, c->counters.p + 8 + ((c->totalSteps + 1) & 1)) > 64;
+  int useIdx = c->NN > 0 && ns > 0 && readInt(c, c->counters.p + 8 + (c->bpSlot ^ 1)) > 64;
   if (useIdx) {  // stable sort of the canonical entries by key1, then by key0
     c->wsKa.ensure(ns + 1); c->wsKb.ensure(ns + 1); c->wsK0s.ensure(ns + 1); c->wsK1s.ensure(ns + 1);
     c->wsIa.ensure(ns + 1); c->wsIb.ensure(ns + 1); c->wsIdx.ensure(ns + 1);
@@ -143,7 +145,7 @@ static void warmStart(am3d_ctx* c) {
   }
   WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,
             c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
-            c->prev.n, c->prev.nSorted, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, c->prev.viol.p, c->prev.lam.p,
+            c->prev.n, c->prev.nSorted, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, postStab ? c->prev.prevViol.p : c->prev.viol.p, c->prev.lam.p,
             useIdx, c->wsK0s.p, c->wsK1s.p, c->wsIdx.p,
             c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
   LAUNCH(c, k_warm_start_plain, nblk(c->cur.n), BLK, c->cur.n, W);

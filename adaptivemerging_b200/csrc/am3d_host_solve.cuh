@@ -81,16 +81,17 @@ struct SolveSet {
 // PGS.solve (PGS.java:73-194).  sweep = false: the full solve over the external contacts with collections as
 // solver bodies (CollisionProcessor.solveLCP :108-137); sweep = true: the single sweep over external + internal
 // contacts with every body on its own (updateInCollections :232-303).
-static void runSolve(am3d_ctx* c, double dt, bool sweep) {
+// post = true: the position-level solve of postStabilization (RigidBodySystem.java:354-377, PGS.java:86-89)
+static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   const am3d_params& P = c->P;
   int nExt = c->bp.n, nInt = sweep ? c->ibp.n : 0;
   int ng = nExt + nInt;
   int ncExt = c->cur.n, ncInt = sweep ? c->icon.n : 0;
   int nc = ncExt + ncInt;
-  if (!sweep) { c->T.pgs_iterations = 0; c->T.pgs_colors = 0; c->T.pgs_kernel_time = 0; }
+  if (!sweep && !post) { c->T.pgs_iterations = 0; c->T.pgs_colors = 0; c->T.pgs_kernel_time = 0; }
   c->lastSolveSweep = sweep;
   c->lastSolveN = 0;
-  (sweep ? c->orderSweep : c->orderFull).clear();
+  (sweep ? c->orderSweep : post ? c->orderPost : c->orderFull).clear();
   if (nc == 0 || ng == 0) return;
   const int *gb1, *gb2, *gcount, *gstart;
   c->swB1.ensure(ng + 1); c->swB2.ensure(ng + 1); c->swCount.ensure(ng + 1); c->swStart.ensure(ng + 1);
@@ -206,7 +207,9 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
     LAUNCH(c, k_assemble, nblk(CS.n, 128), 128, CS.n, CS.bpc.p, sets[k].groupOffset, sets[k].setId, pstart, pcount, chunkFirst, chunkLen, gstart, c->grpPos.p,
            c->sgStart.p, CS.b1.p, CS.b2.p, c->parent.p, sweep ? 1 : 0, CS.pW.p, CS.nW.p, CS.t1W.p, CS.t2W.p, CS.pB1.p, CS.nB1.p,
            CS.t1B1.p, CS.t2B1.p, CS.viol.p, CS.lam.p, CS.state.p, c->x.p, c->R.p, c->v.p, c->w.p, c->force.p, c->torque.p,
-           c->minv.p, c->jinv.p, c->rest.p, dt, P.feedback_stiffness, P.restitution_override, P.restitution, S);
+           c->minv.p, c->jinv.p, c->rest.p, dt,
+           // CollisionProcessor.java:119: the velocity solve drops the Baumgarte term when post-stabilisation is on
+           (!sweep && !post && P.enable_post_stabilization) ? 0.0 : P.feedback_stiffness, post ? 1 : 0, P.restitution_override, P.restitution, S);
   }
   // giant groups (sphere-tree pairs with hundreds of contacts) lead their phases and are solved one warp each
   std::vector<int> giants(c->nColors, 0);
@@ -290,11 +293,13 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep) {
   LAUNCH(c, k_post_solve, nblk(nSolve), BLK, nSolve, S, c->cur.bpc.p, c->cur.lam.p, c->cur.state.p, sweep ? 0 : 1,
          sweep ? (int*)nullptr : c->bp.nActive.p, c->icon.lam.p, c->icon.state.p);
   if (c->recordOrders) {  // tests: keep the Gauss-Seidel sequence for replay on the CPU oracle
-    std::vector<int>& dst = sweep ? c->orderSweep : c->orderFull;
+    std::vector<int>& dst = sweep ? c->orderSweep : post ? c->orderPost : c->orderFull;
     dst.resize(nSolve);
     if (nSolve) CK(cudaMemcpyAsync(dst.data(), c->scSrc.p, nSolve * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
-  if (!sweep) {
+  if (post) {
+    CK(cudaStreamSynchronize(c->stream));
+  } else if (!sweep) {
     LAUNCH(c, k_row_updates, nblk(ng), BLK, ng, S, nScenes, c->iterState.p);
     unsigned long long st[5];
     CK(cudaMemcpyAsync(st, c->iterState.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));

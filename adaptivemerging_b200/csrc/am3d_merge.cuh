@@ -890,6 +890,19 @@ __global__ void k_reclear_top(int ns, int nb, const int* __restrict__ alive, con
 }
 // collections carry their members along (RigidCollection.updateBodiesPositionAndTransformations :898-909,
 // applyVelocitiesToBodies :914-918)
+// RigidCollection.clearBodies :100-105 (postStabilization): EVERY collection, pinned and sleeping ones too, hands its
+// velocity to its members
+__global__ void k_members_take_velocity(int nb, const int* __restrict__ parent, const double* __restrict__ x, double* __restrict__ v,
+                                        double* __restrict__ w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  int p = parent[i];
+  if (p < 0) return;
+  d3 r = vsub(ld3(x + 3 * i), ld3(x + 3 * p));
+  d3 om = ld3(w + 3 * p);
+  st3(v + 3 * i, vadd(ld3(v + 3 * p), vcross(om, r)));
+  st3(w + 3 * i, om);
+}
 __global__ void k_members_follow(int nb, const int* __restrict__ parent, const int* __restrict__ flags, int pushVel, int pushPos,
                                  double* __restrict__ x, double* __restrict__ R, double* __restrict__ v, double* __restrict__ w,
                                  const double* __restrict__ B2CR, const double* __restrict__ B2Ct, const double* __restrict__ jinv0,

@@ -46,6 +46,41 @@ __global__ void k_clear_gravity(int ns, int nb, const int* __restrict__ alive, c
   for (int k = 0; k < DVS; k++) dv[DVS * (size_t)i + k] = 0.0;
 }
 
+// useCoriolis (RigidBodySystem.java:212-229 gyroscopicStabilization, :295-304 applyCoriolis, RigidBody.java:348-354):
+// awake unpinned top-level bodies get massAngular -= dt^2 * Lhat * jinv * Lhat (L = massAngular * omega), then every
+// unpinned body (members of collections included) gets torque -= (massAngular * omega) x omega
+__global__ void k_coriolis(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent, const int* __restrict__ flags,
+                           const double* __restrict__ w, const double* __restrict__ jinv, double* __restrict__ mA,
+                           double* __restrict__ torque, double dt, int topOnly) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  if (i >= nb && !alive[i - nb]) return;
+  bool top = i >= nb || parent[i] < 0;
+  if (topOnly && !top) return;
+  int f = flags[i];
+  d3 om = ld3(w + 3 * i);
+  m3 M = ldm(mA + 9 * i);
+  if (top && !(f & (AM3D_F_PINNED | AM3D_F_SLEEPING))) {
+    d3 L = mtransform(M, om);
+    m3 Lh;
+    Lh.m[0] = 0.; Lh.m[1] = -L.z; Lh.m[2] = L.y;
+    Lh.m[3] = L.z; Lh.m[4] = 0.; Lh.m[5] = -L.x;
+    Lh.m[6] = -L.y; Lh.m[7] = L.x; Lh.m[8] = 0.;
+#pragma unroll
+    for (int k = 0; k < 9; k++) Lh.m[k] = Lh.m[k] * dt;
+    m3 T = mmul(Lh, ldm(jinv + 9 * i));
+    T = mmul(T, Lh);
+#pragma unroll
+    for (int k = 0; k < 9; k++) { T.m[k] = T.m[k] * -1.; M.m[k] = M.m[k] + T.m[k]; }
+    stm(mA + 9 * i, M);
+  }
+  if (!(f & AM3D_F_PINNED)) {
+    d3 tmp = mtransform(M, om);
+    d3 tmp2 = vcross(tmp, om);
+    st3(torque + 3 * i, vsub(ld3(torque + 3 * i), tmp2));
+  }
+}
+
 __device__ __forceinline__ d3 spatialVelocity(const double* x, const double* v, const double* w, int b, const d3& pW) {
   d3 tmp = vsub(pW, ld3(x + 3 * b));
   d3 r = vcross(ld3(w + 3 * b), tmp);
@@ -680,7 +715,7 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
                            const double* __restrict__ R, const double* __restrict__ v, const double* __restrict__ w,
                            const double* __restrict__ force, const double* __restrict__ torque,
                            const double* __restrict__ minv, const double* __restrict__ jinv, const double* __restrict__ rest,
-                           double dt, double feedback, int restOverride, double restVal, SolveArrays S) {
+                           double dt, double feedback, int postStab, int restOverride, double restVal, SolveArrays S) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   int g = cbpc[i];
@@ -730,7 +765,9 @@ __global__ void k_assemble(int nc, const int* __restrict__ cbpc, int groupOffset
   d3 v1 = ld3(v + 3 * a), w1 = ld3(w + 3 * a), v2 = ld3(v + 3 * b), w2 = ld3(w + 3 * b);
   m3 J1 = ldm(jinv + 9 * a), J2 = ldm(jinv + 9 * b);
   double mi1 = minv[a], mi2 = minv[b];
-  {
+  if (postStab) {  // PGS.java:86-89: position-level right-hand side
+    bb[0] = feedback * viol[i];
+  } else {
     d3 tmp = vscaleAdd(mi1 * dt, ld3(force + 3 * a), v1);
 #pragma unroll
     for (int k = 0; k < 3; k++) bb[k] += vdot(tmp, vscale(-1, dir[k]));
@@ -1358,14 +1395,14 @@ __global__ void k_advance_velocities(int ns, int nb, const int* __restrict__ ali
 // RigidBody.advancePositions :427-441 (expRodrigues :382-401) + viscous decay (RigidBodySystem.java:428-436)
 __global__ void k_advance_positions(int ns, int nb, const int* __restrict__ alive, const int* __restrict__ parent,
                                     const int* __restrict__ flags, double* __restrict__ x, double* __restrict__ R,
-                                    const double* __restrict__ v, const double* __restrict__ w,
+                                    const double* __restrict__ v, const double* __restrict__ w, int vstride /* 3, or DVS: move by deltaV */,
                                     const double* __restrict__ jinv0, const double* __restrict__ mA0,
                                     double* __restrict__ jinv, double* __restrict__ mA, double dt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ns) return;
   if (i >= nb ? !alive[i - nb] : parent[i] >= 0) return;
   if (flags[i] & (AM3D_F_PINNED | AM3D_F_SLEEPING)) return;
-  d3 vv = ld3(v + 3 * i), om = ld3(w + 3 * i);
+  d3 vv = ld3(v + (size_t)vstride * i), om = ld3(w + (size_t)vstride * i);
   st3(x + 3 * i, vscaleAdd(dt, vv, ld3(x + 3 * i)));
   double t = vlen(om) * dt;
   m3 Rm = ldm(R + 9 * i);
@@ -1466,6 +1503,11 @@ __global__ void k_bpc_compact(int nbp, const int* __restrict__ alive, const int*
   for (int k = 0; k < 4; k++) { omh[4 * o + k] = mh[4 * b + k]; osh[4 * o + k] = sh[4 * b + k]; }
 }
 
+// CollisionProcessor.clearBodyPairContacts :213-226 on its own (the step folds it into k_bpc_accumulate)
+__global__ void k_bpc_prune(int nbp, const int* __restrict__ nActive, int* __restrict__ alive) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbp && nActive[b] == 0) alive[b] = 0;
+}
 __global__ void k_iota(int n, int* __restrict__ a) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = i;

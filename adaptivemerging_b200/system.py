@@ -205,10 +205,11 @@ class RigidBodySystem:
         self._ck(self._L.am3d_record_orders(self._h, int(on)))
 
     def order(self, which):
-        """Gauss-Seidel sequence (contact identities) of the last full solve (0) / single sweep (1)."""
-        cap = self._L.am3d_num_contacts(self._h, 1) + 1
-        out = np.zeros(cap, CONTACT_DTYPE)
+        """Gauss-Seidel sequence (contact identities) of the last full solve (0) / single sweep (1) / post-stabilisation solve (2)."""
         cnt = C.c_int(0)
+        self._ck(self._L.am3d_download_order(self._h, int(which), None, 0, C.byref(cnt)))  # size query
+        cap = cnt.value + 1
+        out = np.zeros(cap, CONTACT_DTYPE)
         self._ck(self._L.am3d_download_order(self._h, int(which), _p(out), cap, C.byref(cnt)))
         return out[:cnt.value]
 

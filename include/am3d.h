@@ -325,7 +325,8 @@ int am3d_stats(am3d_ctx* ctx, double* out4);
  * collection (Merging.merge, Merging.java:73-163), 1 = it left its collection (Merging.unmerge :215-374) */
 int am3d_num_events(am3d_ctx* ctx);
 int am3d_download_events(am3d_ctx* ctx, int32_t* out /* [capacity*4] */, int capacity, int* count);
-/* tests: record the Gauss-Seidel sequence of every solve; which = 0 last full solve, 1 last single sweep */
+/* tests: record the Gauss-Seidel sequence of every solve; which = 0 last full solve, 1 last single sweep, 2 last
+ * post-stabilisation solve; out = NULL only reports the count */
 int am3d_record_orders(am3d_ctx* ctx, int on);
 int am3d_download_order(am3d_ctx* ctx, int which, am3d_contact* out, int capacity, int* count);
 /* internal body pairs of collections (RigidCollection.bodyPairContacts with inCollection) */

@@ -67,8 +67,9 @@ struct System {
   am3d_timings T;
   int badWarmStarts = 0, badWarmStartsRepaired = 0;
   // externally supplied Gauss-Seidel orders (keys), consumed by the next step
-  std::vector<am3d_contact> orderFull, orderSweep;
-  bool haveOrderFull = false, haveOrderSweep = false;
+  std::vector<am3d_contact> orderFull, orderSweep, orderPost;
+  bool haveOrderFull = false, haveOrderSweep = false, haveOrderPost = false;
+  bool postStabSolve = false;  // PGS.postStabilization of the solve in progress (PGS.java:86-89)
   int orderMismatch = 0;
   int lastIterations = 0;
   long rowUpdates = 0;  // 3 * contacts * iterations of full solves, accumulated
@@ -252,7 +253,8 @@ struct System {
       updateDeltaVwithLambdai(c, c->lambda2, 2, computeInCollection);
     }
     for (Contact* c : list) {
-      computeB(c, dt, feedbackStiffness, computeInCollection, P.restitution_override != 0, P.restitution);
+      if (postStabSolve) { c->bn = feedbackStiffness * c->constraintViolation; c->bt1 = 0.; c->bt2 = 0.; }  // PGS.java:86-89
+      else computeB(c, dt, feedbackStiffness, computeInCollection, P.restitution_override != 0, P.restitution);
       computeJMinvJt(c, computeInCollection);
     }
     int iter = iterations;
@@ -400,7 +402,8 @@ struct System {
       }
     });
     for (Contact* c : list) {
-      computeB(c, dt, feedbackStiffness, cic, P.restitution_override != 0, P.restitution);
+      if (postStabSolve) { c->bn = feedbackStiffness * c->constraintViolation; c->bt1 = 0.; c->bt2 = 0.; }
+      else computeB(c, dt, feedbackStiffness, cic, P.restitution_override != 0, P.restitution);
       computeJMinvJt(c, cic);
     }
     int iter = iterations, executed = 0;
@@ -712,7 +715,7 @@ struct System {
     auto it = lastTimeStepContacts.find(keyOf(c, info));
     return it == lastTimeStepContacts.end() ? nullptr : it->second;
   }
-  static void takeWarm(Contact* contact, Contact* oldContact, bool zeroDonor) {
+  static void takeWarm(Contact* contact, Contact* oldContact, bool zeroDonor, bool postStabilization) {
     contact->newThisTimeStep = false;
     contact->lambda0 = oldContact->lambda0;
     contact->lambda1 = oldContact->lambda1;
@@ -721,17 +724,18 @@ struct System {
     contact->lambda1warm = oldContact->lambda1;
     contact->lambda2warm = oldContact->lambda2;
     if (zeroDonor) { oldContact->lambda0 = 0; oldContact->lambda1 = 0; oldContact->lambda2 = 0; }
-    contact->prevConstraintViolation = oldContact->constraintViolation;
+    // CollisionProcessor.java:569-572, 617-620, 657-660
+    contact->prevConstraintViolation = postStabilization ? oldContact->prevConstraintViolation : oldContact->constraintViolation;
   }
   // vanillaWarmStart :646-665
-  void vanillaWarmStart(Contact* contact) {
+  void vanillaWarmStart(Contact* contact, bool postStabilization) {
     Contact* oldContact = lookup(contact);
-    if (oldContact != nullptr) takeWarm(contact, oldContact, false);
+    if (oldContact != nullptr) takeWarm(contact, oldContact, false, postStabilization);
     else contact->newThisTimeStep = true;
   }
   static bool isBoxGeom(const Body* b) { return b->geom == G_BOX; }
 
-  void warmStart() {
+  void warmStart(bool postStabilization = false) {
     badWarmStarts = 0;
     badWarmStartsRepaired = 0;
     for (BPC* bpc : bodyPairContacts) {
@@ -740,8 +744,8 @@ struct System {
       bool b1IsComp = bpc->body1->geom == G_COMPOSITE, b2IsComp = bpc->body2->geom == G_COMPOSITE;
       if ((b1IsBox && b2IsBox) || (b1IsComp && b2IsBox) || (b1IsBox && b2IsComp) || (b1IsComp && b2IsComp)) {
         for (Contact* contact : bpc->contactList) {
-          if (contact->csb1 != nullptr && !isBoxGeom(contact->csb1)) { vanillaWarmStart(contact); continue; }
-          if (contact->csb2 != nullptr && !isBoxGeom(contact->csb2)) { vanillaWarmStart(contact); }  // falls through (:501-503)
+          if (contact->csb1 != nullptr && !isBoxGeom(contact->csb1)) { vanillaWarmStart(contact, postStabilization); continue; }
+          if (contact->csb2 != nullptr && !isBoxGeom(contact->csb2)) { vanillaWarmStart(contact, postStabilization); }  // falls through (:501-503)
           V3 pNew = contact->body1->B2W().transformP(contact->contactB1);
           V3 pOld;
           Contact* oldContact = lookup(contact);
@@ -766,7 +770,7 @@ struct System {
               oldContact = bestMatchOldContact;
               dist = bestMatchDist;
             }
-            if (dist < 0.05) takeWarm(contact, oldContact, true);
+            if (dist < 0.05) takeWarm(contact, oldContact, true, postStabilization);
             else contact->newThisTimeStep = true;
           } else {
             double bestMatchDist = 1.7976931348623157e308;
@@ -781,7 +785,7 @@ struct System {
             }
             if (bestMatchInfo != -1) {
               badWarmStartsRepaired++;
-              if (bestMatchDist < 0.05) takeWarm(contact, bestMatchOldContact, true);
+              if (bestMatchDist < 0.05) takeWarm(contact, bestMatchOldContact, true, postStabilization);
               // else: newThisTimeStep keeps the value Contact.set gave it (true)
             } else {
               contact->newThisTimeStep = true;
@@ -789,7 +793,7 @@ struct System {
           }
         }
       } else {
-        for (Contact* contact : bpc->contactList) vanillaWarmStart(contact);
+        for (Contact* contact : bpc->contactList) vanillaWarmStart(contact, postStabilization);
       }
     }
   }
@@ -1620,24 +1624,55 @@ struct System {
   }
 
   // solveLCP :108-137
-  void solveLCP(double dt) {
+  void solveLCP(double dt, bool postStabilization = false) {
     if (!contacts.empty()) {
       // the externally supplied sequence only orders the Gauss-Seidel sweeps; `contacts` itself keeps the
       // reference's emission order (it decides which duplicate-key contact the warm-start map retains, :443-448)
       std::vector<Contact*> list = contacts;
       std::vector<OrderMeta> meta;
-      bool hubs = haveOrderFull && applyOrder(list, orderFull, meta);
+      bool haveOrder = postStabilization ? haveOrderPost : haveOrderFull;
+      bool hubs = haveOrder && applyOrder(list, postStabilization ? orderPost : orderFull, meta);
       updateJacobiansThatNeedUpdating(list, false);
+      // :119: the velocity solve drops the Baumgarte term when post-stabilisation takes care of the drift
+      double feedback = (!P.enable_post_stabilization || postStabilization) ? P.feedback_stiffness : 0.;
+      postStabSolve = postStabilization;
       double t0 = nowSec();
-      if (hubs) pgsSolveHub(list, meta, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
-      else pgsSolve(list, dt, P.iterations, P.tolerance, P.omega, P.feedback_stiffness, P.enable_compliance ? P.compliance : 0., false);
-      T.lcp_solve = nowSec() - t0;
-      T.pgs_iterations = lastIterations;
-      rowUpdates += 3L * (long)contacts.size() * lastIterations;
-      solveSeconds += T.lcp_solve;
-    } else {
+      if (hubs) pgsSolveHub(list, meta, dt, P.iterations, P.tolerance, P.omega, feedback, P.enable_compliance ? P.compliance : 0., false);
+      else pgsSolve(list, dt, P.iterations, P.tolerance, P.omega, feedback, P.enable_compliance ? P.compliance : 0., false);
+      postStabSolve = false;
+      if (!postStabilization) {
+        T.lcp_solve = nowSec() - t0;
+        T.pgs_iterations = lastIterations;
+        rowUpdates += 3L * (long)contacts.size() * lastIterations;
+        solveSeconds += T.lcp_solve;
+      }
+    } else if (!postStabilization) {
       T.lcp_solve = 0;
       T.pgs_iterations = 0;
+    }
+  }
+
+  // postStabilization (RigidBodySystem.java:354-377): a second detection at the advanced positions and a position-level
+  // solve whose right-hand side is feedbackStiffness * violation; the bodies are then moved by deltaV
+  void postStabilization(double dt) {
+    for (Body* b : bodies) {
+      b->clear();
+      if (b->isCollection)
+        for (Body* s : b->bodies) { applyVelocitiesTo(b, s); s->clear(); }  // RigidCollection.clearBodies :100-105
+    }
+    updateContactsMap();
+    collisionDetection();
+    updateBodyPairContacts();
+    warmStart(true);
+    solveLCP(dt, true);
+    clearBodyPairContacts();
+    for (Body* b : bodies) {
+      if (b->pinned || b->sleeping) continue;
+      // RigidBody.advancePositionsPostStabilization :423-425 = advancePositions(dt, deltaV.v, deltaV.w)
+      V3 v = b->v, w = b->omega;
+      b->v = b->deltaV.v; b->omega = b->deltaV.w;
+      advancePositions(b, dt);
+      b->v = v; b->omega = w;
     }
   }
 
@@ -1688,8 +1723,41 @@ struct System {
     }
   }
   // applyExternalForces :234-257 (mouse spring / impulse are UI objects above the boundary)
+  // gyroscopicStabilization :212-229
+  void gyroscopicStabilization(double dt) {
+    for (Body* body : bodies) {
+      if (body->pinned || body->sleeping) continue;
+      V3 L = transform(body->massAngular, body->omega);
+      M3 Lhat;
+      Lhat.m00 = 0.; Lhat.m01 = -L.z; Lhat.m02 = L.y;
+      Lhat.m10 = L.z; Lhat.m11 = 0.; Lhat.m12 = -L.x;
+      Lhat.m20 = -L.y; Lhat.m21 = L.x; Lhat.m22 = 0.;
+      Lhat = scaleM(dt, Lhat);
+      M3 Tm = mul(Lhat, body->jinv);
+      Tm = mul(Tm, Lhat);
+      Tm = scaleM(-1., Tm);
+      body->massAngular = addM(body->massAngular, Tm);
+    }
+  }
+  // RigidBody.applyCoriolisTorque :348-354
+  static void applyCoriolisTorque(Body* b) {
+    if (b->pinned) return;
+    V3 tmp = transform(b->massAngular, b->omega);
+    V3 tmp2 = cross(tmp, b->omega);
+    b->torque = sub(b->torque, tmp2);
+  }
+  // applyCoriolis :295-304
+  void applyCoriolis() {
+    for (Body* body : bodies) {
+      applyCoriolisTorque(body);
+      if (body->isCollection)
+        for (Body* b : body->bodies) applyCoriolisTorque(b);
+    }
+  }
+  double curDt = 0.05;
   void applyExternalForces() {
     if (P.use_gravity) applyGravityForce();
+    if (P.use_coriolis) { gyroscopicStabilization(curDt); applyCoriolis(); }  // :239-242
     if (P.springs_enabled)
       for (Spring& s : springs) applySpring(s);
   }
@@ -1754,6 +1822,7 @@ struct System {
     double start = nowSec();
     totalSteps++;
     orderMismatch = 0;
+    curDt = dt;
     clearBodies();
     applyExternalForces();
     updateContactsMap();
@@ -1788,6 +1857,7 @@ struct System {
     T.merging = nowSec() - now;
     for (Body* b : bodies)
       if (!b->pinned && !b->sleeping) advancePositions(b, dt);
+    if (P.enable_post_stabilization) postStabilization(dt);  // :162-163
     now = nowSec();
     if ((totalSteps % P.steps_between_merge) == 0) merge();
     T.merging += nowSec() - now;
@@ -1799,7 +1869,7 @@ struct System {
     T.compute_time = nowSec() - start;
     T.n_bodies = (int)bodies.size();
     T.n_contacts = (int)contacts.size();
-    haveOrderFull = haveOrderSweep = false;
+    haveOrderFull = haveOrderSweep = haveOrderPost = false;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -2072,6 +2142,11 @@ void amo_get_deltav(void* h, double* dv) {
     dv[6 * i] = d.v.x; dv[6 * i + 1] = d.v.y; dv[6 * i + 2] = d.v.z;
     dv[6 * i + 3] = d.w.x; dv[6 * i + 4] = d.w.y; dv[6 * i + 5] = d.w.z;
   }
+}
+void amo_set_next_order_post(void* h, const am3d_contact* post, int n_post) {
+  System* s = (System*)h;
+  s->haveOrderPost = post != nullptr;
+  if (post) s->orderPost.assign(post, post + n_post);
 }
 void amo_set_next_orders(void* h, const am3d_contact* full, int n_full, const am3d_contact* sweep, int n_sweep) {
   System* s = (System*)h;

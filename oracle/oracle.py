@@ -31,7 +31,7 @@ def lib():
         L.amo_create.argtypes = [C.c_void_p, C.c_void_p]
         for name in ["amo_destroy", "amo_set_params", "amo_get_bodies", "amo_set_bodies", "amo_get_timings",
                      "amo_apply_external_forces", "amo_set_lambdas", "amo_get_deltav", "amo_set_next_orders",
-                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order"]:
+                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order", "amo_set_next_order_post"]:
             getattr(L, name).restype = None
         for name in ["amo_row_updates", "amo_solve_seconds"]:
             getattr(L, name).restype = C.c_double
@@ -121,9 +121,11 @@ class Oracle:
         self.L.amo_get_deltav(self.h, _p(dv))
         return dv
 
-    def set_next_orders(self, full=None, sweep=None):
+    def set_next_orders(self, full=None, sweep=None, post=None):
         f = np.ascontiguousarray(full, CONTACT_DTYPE) if full is not None else None
         s = np.ascontiguousarray(sweep, CONTACT_DTYPE) if sweep is not None else None
+        q = np.ascontiguousarray(post, CONTACT_DTYPE) if post is not None else None
+        self.L.amo_set_next_order_post(self.h, _p(q), len(q) if q is not None else 0)
         self.L.amo_set_next_orders(self.h, _p(f), len(f) if f is not None else 0, _p(s), len(s) if s is not None else 0)
 
     def events(self):

@@ -88,8 +88,9 @@ def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
             cpu.add_body_velocity(body, dv, dw)
         gpu.advanceTime(0.05)
         full, sweep = gpu.order(0), gpu.order(1)
+        post = gpu.order(2) if p.enable_post_stabilization else []  # the position-level solve of postStabilization
         gpu.hub_contacts += int((full["hub_mask"] != 0).sum()) + int((sweep["hub_mask"] != 0).sum())
-        cpu.set_next_orders(full=full if len(full) else None, sweep=sweep if len(sweep) else None)
+        cpu.set_next_orders(full=full if len(full) else None, sweep=sweep if len(sweep) else None, post=post if len(post) else None)
         mism = cpu.step(0.05)
         assert mism == 0, f"step {step}: contact lists diverged ({mism} mismatches)"
         g, o = gpu.bodies(), cpu.bodies()

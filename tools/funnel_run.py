@@ -18,6 +18,7 @@ nb = int((blob.a["body_type"] != 1).sum())
 s = RigidBodySystem(0).load(blob, p)
 s.set_option("record_events", 0)
 print(desc, f"| {nb} bodies | scene built and uploaded in {time.time() - t0:.1f} s", flush=True)
+os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
 with open(out, "w") as f:
     f.write(json.dumps({"description": desc, "bodies": nb}) + "\n")
     wall0 = time.time()
