@@ -19,7 +19,8 @@ EXPORTS = [
     "am3d_download_deltav", "am3d_set_lambdas", "am3d_stats", "am3d_download_solve_order", "am3d_mark", "am3d_elapsed_ms",
     "am3d_num_events", "am3d_download_events", "am3d_record_orders", "am3d_download_order", "am3d_num_internal_bpcs",
     "am3d_download_internal_bpcs", "am3d_download_collection", "am3d_set_option", "am3d_add_velocities",
-    "am3d_download_bodies_async", "am3d_wait_download", "am3d_download_list_order",
+    "am3d_download_bodies_async", "am3d_wait_download", "am3d_download_list_order", "am3d_set_body_sleeping",
+    "am3d_activate_body", "am3d_remove_body", "am3d_set_mouse_spring", "am3d_apply_impulse",
 ]
 
 _LIB = None
@@ -51,6 +52,11 @@ def load():
         L.am3d_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.am3d_download_collection.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.am3d_num_contacts.argtypes = [C.c_void_p, C.c_int]
+        L.am3d_set_body_sleeping.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.am3d_activate_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.am3d_remove_body.argtypes = [C.c_void_p, C.c_int]
+        L.am3d_set_mouse_spring.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]
+        L.am3d_apply_impulse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
         for n in ["am3d_destroy", "am3d_sync", "am3d_reset", "am3d_num_bodies", "am3d_num_bpcs", "am3d_total_steps",
                   "am3d_detect", "am3d_num_events", "am3d_num_internal_bpcs"]:
             getattr(L, n).argtypes = [C.c_void_p]

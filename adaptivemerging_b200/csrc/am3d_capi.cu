@@ -12,6 +12,11 @@ static void applyCoriolis(am3d_ctx* c, double dt, int topOnly) {
   if (c->P.use_coriolis)
     LAUNCH(c, k_coriolis, nblk(c->NS), BLK, c->NS, c->NB, c->collAlive.p, c->parent.p, c->flags.p, c->w.p, c->jinv.p, c->mA.p, c->torque.p, dt, topOnly);
 }
+static void applyMouseTools(am3d_ctx* c, int part) {  // RigidBodySystem.java:244-247 (part 0), :249-256 (part 1)
+  if (c->mouseUsed)
+    LAUNCH(c, k_mouse_tools, 1, 32, part, (MouseState*)c->mouse.p, c->parent.p, c->flags.p, c->metricCount.p, c->picked.p, c->x.p, c->R.p, c->v.p,
+           c->w.p, c->force.p, c->torque.p);
+}
 static void applyExternalForces(am3d_ctx* c, double dt) {
   const am3d_params& P = c->P;
   double theta = P.gravity_angle_deg / 180.0 * M_PI;
@@ -19,10 +24,12 @@ static void applyExternalForces(am3d_ctx* c, double dt) {
   LAUNCH(c, k_clear_gravity, nblk(c->NS), BLK, c->NS, c->NB, c->collAlive.p, c->parent.p, c->mass.p, c->x.p, c->v.p, c->w.p,
          c->force.p, c->torque.p, c->dv.p, P.use_gravity, gx, gy);
   applyCoriolis(c, dt, 0);
+  applyMouseTools(c, 0);
   if (P.springs_enabled && c->nSpringBodies > 0)
     LAUNCH(c, k_springs, nblk(c->nSpringBodies, 64), 64, c->nSpringBodies, c->spBodies.p, c->spBodyStart.p, c->spBodyList.p,
            c->spType.p, c->spB1.p, c->spB2.p, c->spPb1.p, c->spPb2.p, c->spPw.p, c->spK.p, c->spD.p, c->spL0.p, c->spLs.p,
            P.spring_k_mod, P.spring_d_mod, c->parent.p, c->x.p, c->R.p, c->v.p, c->w.p, c->force.p, c->torque.p);
+  applyMouseTools(c, 1);
 }
 
 static void applySprings(am3d_ctx* c) {
@@ -205,7 +212,9 @@ static void stepOnce(am3d_ctx* c, double dt) {
     LAUNCH(c, k_reclear_top, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->mass.p, c->force.p, c->torque.p, c->dv.p,
            P.use_gravity, gx, gy);
     applyCoriolis(c, dt, 0);  // applyExternalForces runs again in full: second gyroscopic term, Coriolis torque on members too
+    applyMouseTools(c, 0);
     applySprings(c);
+    applyMouseTools(c, 1);
   }
   CK(cudaEventRecord(c->ev[4], c->stream));
   // redoWarmStart (:146-150): the sweep never writes the multipliers of external contacts back, so lambda == lambdaWarm
@@ -263,7 +272,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
   c->T.merging_build = c->T.merging;
   c->T.unmerging_build = c->T.unmerging;
   c->T.compute_time = evMs(c, 0, 7) * 1e-3;
-  c->T.n_bodies = NB - c->nMergedLeaves + c->nCollections;  // bodies.size(): a collection counts as one (RigidBodySystem.java:503)
+  c->T.n_bodies = NB - c->nDormant - c->nMergedLeaves + c->nCollections;  // bodies.size(): a collection counts as one (RigidBodySystem.java:503)
   c->T.n_contacts = c->cur.n;  // collision.contacts.size() at the end of the step, unmerge-appended contacts included
   c->T.n_collections = c->nCollections;
 }
@@ -485,7 +494,7 @@ __global__ void k_body_flags_out(int nb, const int* __restrict__ parent, const i
   if (i >= nb) return;
   int p = parent[i];
   int t = p >= 0 ? p : i;
-  sleeping[i] = (flags[t] & AM3D_F_SLEEPING) ? 1 : 0;
+  sleeping[i] = ((flags[t] & AM3D_F_SLEEPING) && !(flags[t] & AM3D_F_DORMANT)) ? 1 : 0;  // (dormant bodies carry the flag only to stay out of the integrator)
   collection[i] = p >= 0 ? p - nb : -1;
 }
 static void downloadBodies(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
@@ -574,6 +583,95 @@ int am3d_add_body_velocity(am3d_ctx* c, int body, const double dv[3], const doub
     for (int k = 0; k < 3; k++) cur[k] = cur[k] + domega[k];
     CK(cudaMemcpy(c->w.p + 3 * t, cur, sizeof(cur), cudaMemcpyHostToDevice));
   }
+  API_END(c)
+}
+
+int am3d_set_body_sleeping(am3d_ctx* c, int body, int sleeping) {
+  API_BEGIN(c)
+  if (!c->haveScene || body < 0 || body >= c->NB) throw AmError(AM3D_EINVAL, "bad body index");
+  int fl;
+  CK(cudaMemcpy(&fl, c->flags.p + body, sizeof(int), cudaMemcpyDeviceToHost));
+  fl = sleeping ? (fl | AM3D_F_SLEEPING) : (fl & ~AM3D_F_SLEEPING);
+  CK(cudaMemcpy(c->flags.p + body, &fl, sizeof(int), cudaMemcpyHostToDevice));
+  API_END(c)
+}
+
+// one body: state, world-frame inertia, flags as in the scene blob minus DORMANT, list position at the end
+__global__ void k_activate_body(int b, int flagsOn, long long stampNew, const double* __restrict__ st /* x3 R9 v3 w3 */, double* __restrict__ x,
+                                double* __restrict__ R, double* __restrict__ v, double* __restrict__ w, int* __restrict__ flags,
+                                long long* __restrict__ stamp, int* __restrict__ metricCount, const double* __restrict__ jinv0,
+                                const double* __restrict__ mA0, double* __restrict__ jinv, double* __restrict__ mA) {
+  if (blockIdx.x || threadIdx.x) return;
+  for (int k = 0; k < 3; k++) { x[3 * b + k] = st[k]; v[3 * b + k] = st[12 + k]; w[3 * b + k] = st[15 + k]; }
+  for (int k = 0; k < 9; k++) R[9 * b + k] = st[3 + k];
+  flags[b] = flagsOn;
+  stamp[b] = stampNew;
+  metricCount[b] = 0;
+  if (!(flagsOn & AM3D_F_PINNED)) {  // RigidBody.updateRotationalInertiaFromTransformation :311-321
+    m3 Rm = ldm(R + 9 * b);
+    stm(mA + 9 * b, rm0rt(Rm, ldm(mA0 + 9 * b)));
+    stm(jinv + 9 * b, rm0rt(Rm, ldm(jinv0 + 9 * b)));
+  }
+}
+int am3d_activate_body(am3d_ctx* c, int body, const double x[3], const double R[9], const double v[3], const double omega[3]) {
+  API_BEGIN(c)
+  if (!c->haveScene || body < 0 || body >= c->NB || !x) throw AmError(AM3D_EINVAL, "bad body index / null position");
+  int fl;
+  CK(cudaMemcpy(&fl, c->flags.p + body, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!(fl & AM3D_F_DORMANT)) throw AmError(AM3D_ESTATE, "body is already part of the simulation");
+  double st[18] = {x[0], x[1], x[2], 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0};
+  if (R) for (int k = 0; k < 9; k++) st[3 + k] = R[k];
+  if (v) for (int k = 0; k < 3; k++) st[12 + k] = v[k];
+  if (omega) for (int k = 0; k < 3; k++) st[15 + k] = omega[k];
+  c->pokeV.ensure(18);
+  CK(cudaMemcpyAsync(c->pokeV.p, st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  int on = c->H.body_flags[body] & ~(AM3D_F_DORMANT | AM3D_F_SLEEPING);
+  if (c->H.body_type[body] == AM3D_BODY_PLANE) on |= AM3D_F_PINNED;
+  LAUNCH(c, k_activate_body, 1, 32, body, on, c->nextStamp, c->pokeV.p, c->x.p, c->R.p, c->v.p, c->w.p, c->flags.p, c->stamp.p, c->metricCount.p,
+         c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p);
+  c->nextStamp++;
+  c->nDormant--;
+  CK(cudaStreamSynchronize(c->stream));
+  API_END(c)
+}
+int am3d_remove_body(am3d_ctx* c, int body) {
+  API_BEGIN(c)
+  if (!c->haveScene || body < 0 || body >= c->NB) throw AmError(AM3D_EINVAL, "bad body index");
+  int fl, par;
+  CK(cudaMemcpy(&fl, c->flags.p + body, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&par, c->parent.p + body, sizeof(int), cudaMemcpyDeviceToHost));
+  if (fl & AM3D_F_DORMANT) throw AmError(AM3D_ESTATE, "body is not part of the simulation");
+  if (par >= 0) throw AmError(AM3D_ESTATE, "body is part of a collection");
+  fl |= AM3D_F_DORMANT | AM3D_F_PINNED | AM3D_F_SLEEPING;
+  CK(cudaMemcpy(c->flags.p + body, &fl, sizeof(int), cudaMemcpyHostToDevice));
+  c->nDormant++;
+  API_END(c)
+}
+int am3d_set_mouse_spring(am3d_ctx* c, int body, const double grabPointB[3], const double pointW[3], double stiffness, double damping,
+                          int apply_at_com) {
+  API_BEGIN(c)
+  if (!c->haveScene || body >= c->NB) throw AmError(AM3D_EINVAL, "bad body index");
+  if (body >= 0 && (!grabPointB || !pointW)) throw AmError(AM3D_EINVAL, "null points");
+  MouseState ms;
+  CK(cudaMemcpy(&ms, c->mouse.p, sizeof(ms), cudaMemcpyDeviceToHost));
+  ms.springBody = body < 0 ? -1 : body;
+  if (body >= 0) {
+    for (int k = 0; k < 3; k++) { ms.grabB[k] = grabPointB[k]; ms.pointW[k] = pointW[k]; }
+    ms.k = stiffness; ms.c = damping; ms.atCOM = apply_at_com;
+    c->mouseUsed = true;
+  }
+  CK(cudaMemcpy(c->mouse.p, &ms, sizeof(ms), cudaMemcpyHostToDevice));
+  API_END(c)
+}
+int am3d_apply_impulse(am3d_ctx* c, int body, const double pickedPointB[3], const double endPointW[3], double scale) {
+  API_BEGIN(c)
+  if (!c->haveScene || body < 0 || body >= c->NB || !pickedPointB || !endPointW) throw AmError(AM3D_EINVAL, "bad body index / null points");
+  MouseState ms;
+  CK(cudaMemcpy(&ms, c->mouse.p, sizeof(ms), cudaMemcpyDeviceToHost));
+  ms.impBody = body; ms.impPhase = 1; ms.impScale = scale;
+  for (int k = 0; k < 3; k++) { ms.impPointB[k] = pickedPointB[k]; ms.impEndW[k] = endPointW[k]; }
+  CK(cudaMemcpy(c->mouse.p, &ms, sizeof(ms), cudaMemcpyHostToDevice));
+  c->mouseUsed = true;
   API_END(c)
 }
 

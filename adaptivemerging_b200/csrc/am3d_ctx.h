@@ -212,6 +212,10 @@ struct am3d_ctx {
   BpcSet ibp, ibp2;         // internal body pairs (BodyPairContact.inCollection == true)
   DevBuf<int> ibpCut, ibpCut2;
   DevBuf<double> pokeV, pokeW;
+  DevBuf<unsigned char> mouse;  // one MouseState (am3d_step.cuh): mouse spring + impulse of the UI
+  DevBuf<int> picked;           // RigidBody.picked per leaf
+  bool mouseUsed = false;
+  int nDormant = 0;             // bodies of the blob that are not in RigidBodySystem.bodies (AM3D_F_DORMANT)
   DevBuf<unsigned long long> tailKey, tailKeySorted;
   DevBuf<int> tailVal, tailIdx;
   DevBuf<unsigned long long> wsKa, wsKb, wsK0s, wsK1s;  // (key0,key1)-sorted index of last step's contacts

@@ -127,6 +127,7 @@ __device__ __forceinline__ void tryPair(const PairCtx& C, int sa, int sb) {
   int tb = C.parent[bb] >= 0 ? C.parent[bb] : bb;
   if (ta == tb) return;
   int fa = C.flags[ta], fb = C.flags[tb];
+  if ((fa | fb) & AM3D_F_DORMANT) return;  // not in RigidBodySystem.bodies
   bool pa = fa & AM3D_F_PINNED, pb = fb & AM3D_F_PINNED;
   if (pa && pb) return;
   if ((pa && (fb & AM3D_F_SLEEPING)) || (pb && (fa & AM3D_F_SLEEPING))) return;

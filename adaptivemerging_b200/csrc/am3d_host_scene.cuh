@@ -1,6 +1,7 @@
 // Scene upload and reset: RigidBodySystem.reset() (RigidBodySystem.java:390-426) on the device arrays.
 #pragma once
 #include "am3d_host_util.cuh"
+#include "am3d_step.cuh"
 // ------------------------------------------------------------------------------------------------
 static void copyScene(am3d_ctx* c, const am3d_scene* s) {
   auto& H = c->H;
@@ -56,9 +57,22 @@ static void resetState(am3d_ctx* c) {
   h2dv(c, c->fric, padD(H.body_fric, 1)); h2dv(c, c->rest, padD(H.body_rest, 1)); h2dv(c, c->bbB, padD(H.body_bbB, 24));
   h2dv(c, c->bbCount, padI(H.body_bb_count, 0));
   std::vector<int> fl = H.body_flags;
+  c->nDormant = 0;
   for (int i = 0; i < NB; i++) {
     fl[i] &= ~AM3D_F_SLEEPING;
     if (H.body_type[i] == AM3D_BODY_PLANE) fl[i] |= AM3D_F_PINNED;
+    if (fl[i] & AM3D_F_DORMANT) { fl[i] |= AM3D_F_PINNED | AM3D_F_SLEEPING; c->nDormant++; }  // neither integrated nor collided
+  }
+  c->picked.ensure(NB + 1);
+  CK(cudaMemsetAsync(c->picked.p, 0, (NB + 1) * sizeof(int), c->stream));
+  {
+    MouseState ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.springBody = -1;
+    c->mouse.ensure(sizeof(MouseState));
+    CK(cudaMemcpyAsync(c->mouse.p, &ms, sizeof(ms), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->mouseUsed = false;
   }
   h2dv(c, c->flags, padI(fl, 0));
   h2dv(c, c->scene, padI(H.body_scene, 0));

@@ -110,6 +110,10 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
     CK(cudaMemsetAsync(c->bodyLevel.p, 0x7f, c->NB * sizeof(int), c->stream));
     CK(cudaMemsetAsync(c->bfsRound.p, 0, 8 * sizeof(int), c->stream));
     if (ncExt > 0) LAUNCH(c, k_bfs_seed, nblk(ncExt), BLK, ncExt, c->cur.isNew.p, c->cur.bpc.p, c->grpLayer.p);
+    if (c->mouseUsed) {
+      LAUNCH(c, k_bfs_seed_picked, nblk(ng), BLK, ng, gb1, gb2, gcount, c->picked.p, c->grpLayer.p);
+      CK(cudaMemsetAsync(c->picked.p, 0, c->NB * sizeof(int), c->stream));  // b.picked = false (:371, :380)
+    }
     {
       int ngv = ng;
       int *gl = c->grpLayer.p, *bl = c->bodyLevel.p, *rd = c->bfsRound.p;

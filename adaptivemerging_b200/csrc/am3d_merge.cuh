@@ -774,6 +774,14 @@ __global__ void k_bfs_seed(int nc, const int* __restrict__ isNew, const int* __r
   if (i >= nc) return;
   if (isNew[i] && cbpc[i] >= 0) grpLayer[cbpc[i]] = 0;
 }
+// body pairs of the bodies the user interacted with (RigidBody.picked, set by the mouse tools) come right after the
+// pairs with new contacts (CollisionProcessor.java:361-383): class 1; the breadth-first layers follow as classes 2, 3, ...
+__global__ void k_bfs_seed_picked(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ gcount,
+                                  const int* __restrict__ picked, int* __restrict__ grpLayer) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng || gcount[g] == 0 || grpLayer[g] == 0) return;
+  if (picked[gb1[g]] || picked[gb2[g]]) grpLayer[g] = 1;
+}
 // cooperative: one grid barrier per layer.  round[3] = "something was reached" flags, rotating; round[3] = deepest layer
 __global__ void __launch_bounds__(256)
 k_bfs_layers(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, const int* __restrict__ gcount,
@@ -781,9 +789,9 @@ k_bfs_layers(int ng, const int* __restrict__ gb1, const int* __restrict__ gb2, c
   cg::grid_group grid = cg::this_grid();
   int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
   for (int g = tid; g < ng; g += stride)
-    if (gcount[g] > 0 && grpLayer[g] == 0) { atomicMin(bodyLevel + gb1[g], 0); atomicMin(bodyLevel + gb2[g], 0); }
+    if (gcount[g] > 0 && grpLayer[g] <= 1) { atomicMin(bodyLevel + gb1[g], 1); atomicMin(bodyLevel + gb2[g], 1); }  // seeds: classes 0 and 1
   grid.sync();
-  for (int L = 1;; L++) {
+  for (int L = 2;; L++) {
     if (tid == 0) round[(L + 1) % 3] = 0;
     bool any = false;
     for (int g = tid; g < ng; g += stride) {

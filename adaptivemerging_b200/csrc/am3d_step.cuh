@@ -99,6 +99,73 @@ __device__ __forceinline__ void applyForceW(double* force, double* torque, const
   }
 }
 
+// Mouse tools (one thread): MouseSpringForce.apply (MouseSpringForce.java:69-101) and MouseImpulse.apply / Impulse
+// (MouseImpulse.java:101-125, RigidBodySystem.java:249-267) as applyExternalForces runs them, before the scene's springs
+struct MouseState {
+  int springBody;  // -1: none
+  int atCOM;
+  int impBody;
+  int impPhase;    // 0 none, 1 released (apply at the next applyExternalForces), 2 holding the force for one more application
+  double grabB[3], pointW[3], k, c;
+  double impPointB[3], impEndW[3], impScale;
+  double heldPointW[3], heldForce[3];
+};
+__device__ __forceinline__ void wakeBody(int i, int* flags, int* metricCount);
+__global__ void k_mouse_tools(int part /* 0: mouse spring (before the scene's springs), 1: impulse (after them) */, MouseState* M, const int* __restrict__ parent, int* __restrict__ flags, int* __restrict__ metricCount,
+                              int* __restrict__ picked, const double* __restrict__ x, const double* __restrict__ R,
+                              const double* __restrict__ v, const double* __restrict__ w, double* __restrict__ force,
+                              double* __restrict__ torque) {
+  if (blockIdx.x || threadIdx.x) return;
+  if (part == 0 && M->springBody >= 0) {
+    int b = M->springBody, p = parent[b];
+    wakeBody(b, flags, metricCount);
+    if (p >= 0) wakeBody(p, flags, metricCount);
+    picked[b] = 1;
+    xf T;
+    T.R = ldm(R + 9 * b); T.t = ld3(x + 3 * b);
+    d3 gW = xfP(T, ld3(M->grabB)), pW = ld3(M->pointW);
+    d3 dd = vsub(gW, pW);
+    double distance = sqrt(dd.x * dd.x + dd.y * dd.y + dd.z * dd.z);
+    d3 dir = vsub(pW, gW);
+    if (dir.x * dir.x + dir.y * dir.y + dir.z * dir.z >= 1e-3) {
+      dir = vnormalize(dir);
+      d3 at = M->atCOM ? ld3(x + 3 * b) : gW;
+      d3 f = vscale(distance * M->k, dir);
+      if (p >= 0) applyForceW(force, torque, x, p, gW, f, false);
+      applyForceW(force, torque, x, b, at, f, false);
+      d3 gv = spatialVelocity(x, v, w, b, gW);
+      f = vscale(-vdot(gv, dir) * M->c, dir);
+      if (p >= 0) applyForceW(force, torque, x, p, gW, f, false);
+      applyForceW(force, torque, x, b, at, f, false);
+    }
+  }
+  if (part == 0) return;
+  if (M->impPhase == 1) {
+    int b = M->impBody, p = parent[b];
+    wakeBody(b, flags, metricCount);
+    if (p >= 0) wakeBody(p, flags, metricCount);
+    picked[b] = 1;
+    xf T;
+    T.R = ldm(R + 9 * b); T.t = ld3(x + 3 * b);
+    d3 pW = xfP(T, ld3(M->impPointB)), eW = ld3(M->impEndW);
+    d3 dd = vsub(eW, pW);
+    double distance = sqrt(dd.x * dd.x + dd.y * dd.y + dd.z * dd.z);
+    d3 dir = vsub(pW, eW);
+    M->impPhase = 0;
+    if (dir.x * dir.x + dir.y * dir.y + dir.z * dir.z >= 1e-3) {
+      dir = vnormalize(dir);
+      d3 f = vscale(M->impScale * distance, dir);
+      if (p >= 0) applyForceW(force, torque, x, p, pW, f, false);
+      applyForceW(force, torque, x, b, pW, f, false);
+      st3(M->heldPointW, pW); st3(M->heldForce, f);
+      M->impPhase = 2;
+    }
+  } else if (M->impPhase == 2) {  // RigidBodySystem.applyImpulse :262-267
+    applyForceW(force, torque, x, M->impBody, ld3(M->heldPointW), ld3(M->heldForce), false);
+    M->impPhase = 0;
+  }
+}
+
 // One thread per body that has springs; its (spring, side) entries are visited in spring-list order so
 // the accumulation order into force/torque is the reference's (applySpringForces :309-323).
 __global__ void k_springs(int nsb, const int* __restrict__ spBodies, const int* __restrict__ start,

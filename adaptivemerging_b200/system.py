@@ -162,6 +162,28 @@ class RigidBodySystem:
         w = np.ascontiguousarray(domega, np.float64) if domega is not None else None
         self._ck(self._L.am3d_add_body_velocity(self._h, int(body), _p(v), _p(w)))
 
+    # -- Factory / UI hooks (RigidBodySystem.add / remove, MouseSpringForce, MouseImpulse, Animation) ----------------
+    def set_body_sleeping(self, body, sleeping):
+        self._ck(self._L.am3d_set_body_sleeping(self._h, int(body), int(bool(sleeping))))
+
+    def activate_body(self, body, x, R=None, v=None, omega=None):
+        """RigidBodySystem.add of a dormant clone (Factory.generateBody)"""
+        a = [np.ascontiguousarray(q, np.float64) if q is not None else None for q in (x, R, v, omega)]
+        self._ck(self._L.am3d_activate_body(self._h, int(body), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3])))
+
+    def remove_body(self, body):
+        self._ck(self._L.am3d_remove_body(self._h, int(body)))
+
+    def set_mouse_spring(self, body, grab_point_b=None, point_w=None, stiffness=50.0, damping=10.0, at_com=False):
+        g = np.ascontiguousarray(grab_point_b, np.float64) if grab_point_b is not None else None
+        w = np.ascontiguousarray(point_w, np.float64) if point_w is not None else None
+        self._ck(self._L.am3d_set_mouse_spring(self._h, -1 if body is None else int(body), _p(g), _p(w), float(stiffness), float(damping), int(at_com)))
+
+    def apply_impulse(self, body, picked_point_b, end_point_w, scale=1.0):
+        g = np.ascontiguousarray(picked_point_b, np.float64)
+        w = np.ascontiguousarray(end_point_w, np.float64)
+        self._ck(self._L.am3d_apply_impulse(self._h, int(body), _p(g), _p(w), float(scale)))
+
     def add_velocities(self, dv, domega):
         """bulk velocity pokes, [n,3] each (the batched form of MouseImpulse / scripted pushes)"""
         dv = np.ascontiguousarray(dv, np.float64)
@@ -226,11 +248,12 @@ class RigidBodySystem:
         return dict(x=out[0:3], R=out[3:12], v=out[12:15], omega=out[15:18], mass=out[18], minv=out[19], jinv=out[20:29],
                     mA=out[29:38], flags=int(out[38]), alive=int(out[39]), count=int(out[40]), stamp=int(out[41]))
 
-    def list_order(self):
-        """rank of every leaf body's top-level entity in RigidBodySystem.bodies (0 = first in the list)"""
+    def list_order(self, raw=False):
+        """rank of every leaf body's top-level entity in RigidBodySystem.bodies (0 = first in the list); raw: the monotone
+        position keys themselves (dormant bodies carry a stale key)"""
         out = np.zeros(self.n_bodies, np.int64)
         self._ck(self._L.am3d_download_list_order(self._h, _p(out)))
-        return np.unique(out, return_inverse=True)[1]
+        return out if raw else np.unique(out, return_inverse=True)[1]
 
     def set_option(self, name, value):
         self._ck(self._L.am3d_set_option(self._h, name.encode(), float(value)))

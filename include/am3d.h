@@ -57,6 +57,9 @@ extern "C" {
 #define AM3D_F_MAGNETIC 2
 #define AM3D_F_MAGNET_ACTIVE 4
 #define AM3D_F_SLEEPING 8
+/* a body that is in the scene blob but not (yet) in RigidBodySystem.bodies: a pre-allocated clone of a factory part
+ * (Factory.generateBody, Factory.java:99-116) waiting for am3d_activate_body, or a body taken out by am3d_remove_body */
+#define AM3D_F_DORMANT 16
 
 /* spring types: Spring.java:31 */
 #define AM3D_SPRING_ZERO 0
@@ -282,6 +285,24 @@ int am3d_sync(am3d_ctx* ctx);
  * (LCPApp3D scripted pushes, MouseImpulse, Animation) */
 int am3d_set_body_velocity(am3d_ctx* ctx, int body, const double v[3], const double omega[3]);
 int am3d_add_body_velocity(am3d_ctx* ctx, int body, const double dv[3], const double domega[3]);
+/* Animation.applyNonPersistant (Animation.java:82-160) writes `body.sleeping = false` next to the velocity it sets */
+int am3d_set_body_sleeping(am3d_ctx* ctx, int body, int sleeping);
+/* RigidBodySystem.add(body) (:78) as Factory.generateBody uses it (Factory.java:99-116): a DORMANT body of the scene blob
+ * (a clone of a factory part) enters RigidBodySystem.bodies at the end of the list with the given state.
+ * R = NULL: identity, v / omega = NULL: zero. */
+int am3d_activate_body(am3d_ctx* ctx, int body, const double x[3], const double R[9], const double v[3], const double omega[3]);
+/* RigidBodySystem.remove(body) (:383): the body leaves the simulation (it must not be part of a collection) */
+int am3d_remove_body(am3d_ctx* ctx, int body);
+/* MouseSpringForce (MouseSpringForce.java:69-101): a spring between the point grabPointB of `body` and the world point
+ * pointW, applied in every applyExternalForces (RigidBodySystem.java:244-247) until released with body = -1.  The body
+ * is woken and marked as picked (its body pairs lead the single sweep, CollisionProcessor.java:361-383). */
+int am3d_set_mouse_spring(am3d_ctx* ctx, int body, const double grabPointB[3], const double pointW[3], double stiffness,
+                          double damping, int apply_at_com);
+/* MouseImpulse.apply (MouseImpulse.java:101-125) + Impulse (RigidBodySystem.java:249-267): at the next step a force
+ * scale * |end - picked| along (picked - end) acts at pickedPointB on the body and its collection; the step after that
+ * (or the re-application of the forces after a merge event) applies the stored force once more to the body alone, as
+ * the reference does */
+int am3d_apply_impulse(am3d_ctx* ctx, int body, const double pickedPointB[3], const double endPointW[3], double scale);
 /* bulk version: per-body velocity increments [3n] each (zeros are skipped), added to the top-level entity */
 int am3d_add_velocities(am3d_ctx* ctx, const double* dv, const double* domega);
 int am3d_upload_bodies(am3d_ctx* ctx, const double* x, const double* R, const double* v,

@@ -1494,7 +1494,7 @@ struct System {
         for (int i = 0; i < 2; i++) {
           Body* body = bpc->getBody(i);
           for (BPC* other : body->bodyPairContacts) {
-            if (!other->checked) { next.push_back(other); other->checked = true; other->layer = depth; }
+            if (!other->checked) { next.push_back(other); other->checked = true; other->layer = 1 + depth; }  // classes: 0 new, 1 picked, 2.. layers
           }
         }
       }
@@ -1514,14 +1514,24 @@ struct System {
         if (c->newThisTimeStep) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = 0; break; }
       }
     }
-    // (picked bodies: UI only, never set here)
+    // second: all bpc of bodies the user interacted with (:361-383)
+    auto takePicked = [&](Body* b) {
+      if (!b->picked) return;
+      for (BPC* bpc : b->bodyPairContacts)
+        if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = 1; }
+      b->picked = false;
+    };
+    for (Body* body : bodies) {
+      if (body->isCollection) { for (Body* b : body->bodies) takePicked(b); }
+      else takePicked(body);
+    }
     if (!ordered.empty()) getNextLayer(ordered, ordered);
     for (BPC* bpc : bodyPairContacts)
-      if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 1; }
+      if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 2; }
     for (Body* body : bodies) {
       if (body->isCollection && !body->sleeping) {
         for (BPC* bpc : body->bodyPairContacts)
-          if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 2; }
+          if (!bpc->checked) { ordered.push_back(bpc); bpc->checked = true; bpc->layer = lastDepth + 3; }
       }
     }
     for (BPC* bpc : ordered)
@@ -1755,11 +1765,66 @@ struct System {
     }
   }
   double curDt = 0.05;
+  // the UI's mouse tools as the step sees them
+  struct Mouse {
+    Body* springBody = nullptr;
+    V3 grabB, pointW;
+    double k = 50, c = 10;
+    bool atCOM = false;
+    Body* impBody = nullptr;
+    int impPhase = 0;  // 1 released, 2 Impulse.holdingForce
+    V3 impPointB, impEndW, heldPointW, heldForce;
+    double impScale = 1;
+  } mouse;
+  // MouseSpringForce.apply :69-101
+  void mouseSpringApply() {
+    Body* picked = mouse.springBody;
+    if (picked == nullptr) return;
+    wake(picked);
+    picked->picked = true;
+    V3 grabPointBW = picked->B2W().transformP(mouse.grabB);
+    double dist = distance(grabPointBW, mouse.pointW);
+    V3 direction = sub(mouse.pointW, grabPointBW);
+    if (dot(direction, direction) < 1e-3) return;
+    direction = normalize(direction);
+    V3 force = scale(dist * mouse.k, direction);
+    if (picked->isInCollection()) applyForceW(picked->parent, grabPointBW, force);
+    applyForceW(picked, mouse.atCOM ? picked->x : grabPointBW, force);
+    V3 grabPointV = getSpatialVelocity(picked, grabPointBW);
+    force = scale(-dot(grabPointV, direction) * mouse.c, direction);
+    if (picked->isInCollection()) applyForceW(picked->parent, grabPointBW, force);
+    applyForceW(picked, mouse.atCOM ? picked->x : grabPointBW, force);
+  }
+  // RigidBodySystem.java:249-256 with MouseImpulse.apply :101-125 and applyImpulse :262-267
+  void mouseImpulseApply() {
+    if (mouse.impPhase == 1) {
+      Body* b = mouse.impBody;
+      wake(b);
+      b->picked = true;
+      V3 pickedPointW = b->B2W().transformP(mouse.impPointB);
+      double dist = distance(mouse.impEndW, pickedPointW);
+      V3 direction = sub(pickedPointW, mouse.impEndW);
+      mouse.impPhase = 0;
+      if (dot(direction, direction) < 1e-3) return;
+      direction = normalize(direction);
+      V3 force = scale(mouse.impScale * dist, direction);
+      if (b->isInCollection()) applyForceW(b->parent, pickedPointW, force);
+      applyForceW(b, pickedPointW, force);
+      mouse.heldPointW = pickedPointW;
+      mouse.heldForce = force;
+      mouse.impPhase = 2;
+    } else if (mouse.impPhase == 2) {
+      applyForceW(mouse.impBody, mouse.heldPointW, mouse.heldForce);
+      mouse.impPhase = 0;
+    }
+  }
   void applyExternalForces() {
     if (P.use_gravity) applyGravityForce();
     if (P.use_coriolis) { gyroscopicStabilization(curDt); applyCoriolis(); }  // :239-242
+    mouseSpringApply();
     if (P.springs_enabled)
       for (Spring& s : springs) applySpring(s);
+    mouseImpulseApply();
   }
   // clearBodies :190-202, RigidCollection.clearBodies :100-105
   void clearBodies() {
@@ -1939,7 +2004,7 @@ struct System {
         // XML-pinned bodies keep massAngular as computed before the <pinned> tag; it is never read again
         b->jinv.setZero();
       }
-      bodies.push_back(b);
+      if (!(s->body_flags[i] & AM3D_F_DORMANT)) bodies.push_back(b);  // dormant: a factory clone not yet generated
     }
     for (int i = 0; i < s->n_springs; i++) {
       Spring sp;
@@ -2172,6 +2237,43 @@ void amo_add_body_velocity(void* h, int body, const double* dv, const double* do
   amo::Body* t = b->parent ? b->parent : b;
   if (dv) t->v = amo::add(t->v, amo::V3(dv[0], dv[1], dv[2]));
   if (domega) t->omega = amo::add(t->omega, amo::V3(domega[0], domega[1], domega[2]));
+}
+void amo_set_body_sleeping(void* h, int body, int sleeping) { ((System*)h)->leaf[body]->sleeping = sleeping != 0; }
+// RigidBodySystem.add (:78) of a dormant body (Factory.generateBody, Factory.java:99-116)
+void amo_activate_body(void* h, int body, const double* x, const double* R, const double* v, const double* omega) {
+  System* s = (System*)h;
+  amo::Body* b = s->leaf[body].get();
+  b->x = amo::V3(x[0], x[1], x[2]);
+  if (R) b->theta.load(R); else b->theta.setIdentity();
+  b->v = v ? amo::V3(v[0], v[1], v[2]) : amo::V3();
+  b->omega = omega ? amo::V3(omega[0], omega[1], omega[2]) : amo::V3();
+  b->sleeping = false;
+  b->metricHistory.clear();
+  if (!b->pinned) System::updateRotationalInertiaFromTransformation(b);
+  s->bodies.push_back(b);
+}
+// RigidBodySystem.remove (:383)
+void amo_remove_body(void* h, int body) {
+  System* s = (System*)h;
+  amo::Body* b = s->leaf[body].get();
+  s->bodies.erase(std::remove(s->bodies.begin(), s->bodies.end(), b), s->bodies.end());
+}
+void amo_set_mouse_spring(void* h, int body, const double* grabB, const double* pointW, double k, double c, int atCOM) {
+  System* s = (System*)h;
+  s->mouse.springBody = body < 0 ? nullptr : s->leaf[body].get();
+  if (body >= 0) {
+    s->mouse.grabB = amo::V3(grabB[0], grabB[1], grabB[2]);
+    s->mouse.pointW = amo::V3(pointW[0], pointW[1], pointW[2]);
+    s->mouse.k = k; s->mouse.c = c; s->mouse.atCOM = atCOM != 0;
+  }
+}
+void amo_apply_impulse(void* h, int body, const double* pointB, const double* endW, double scale) {
+  System* s = (System*)h;
+  s->mouse.impBody = s->leaf[body].get();
+  s->mouse.impPhase = 1;
+  s->mouse.impPointB = amo::V3(pointB[0], pointB[1], pointB[2]);
+  s->mouse.impEndW = amo::V3(endW[0], endW[1], endW[2]);
+  s->mouse.impScale = scale;
 }
 double amo_row_updates(void* h) { return (double)((System*)h)->rowUpdates; }
 double amo_solve_seconds(void* h) { return ((System*)h)->solveSeconds; }

@@ -31,12 +31,16 @@ def lib():
         L.amo_create.argtypes = [C.c_void_p, C.c_void_p]
         for name in ["amo_destroy", "amo_set_params", "amo_get_bodies", "amo_set_bodies", "amo_get_timings",
                      "amo_apply_external_forces", "amo_set_lambdas", "amo_get_deltav", "amo_set_next_orders",
-                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order", "amo_set_next_order_post"]:
+                     "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order", "amo_set_next_order_post",
+                     "amo_set_body_sleeping", "amo_activate_body", "amo_remove_body", "amo_set_mouse_spring", "amo_apply_impulse"]:
             getattr(L, name).restype = None
         for name in ["amo_row_updates", "amo_solve_seconds"]:
             getattr(L, name).restype = C.c_double
             getattr(L, name).argtypes = [C.c_void_p]
         L.amo_step.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.amo_set_mouse_spring.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]
+        L.amo_apply_impulse.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double]
+        L.amo_activate_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.amo_solve.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
@@ -143,6 +147,26 @@ class Oracle:
         v = np.ascontiguousarray(dv, np.float64) if dv is not None else None
         w = np.ascontiguousarray(domega, np.float64) if domega is not None else None
         self.L.amo_add_body_velocity(self.h, body, _p(v), _p(w))
+
+    def set_body_sleeping(self, body, sleeping):
+        self.L.amo_set_body_sleeping(self.h, int(body), int(bool(sleeping)))
+
+    def activate_body(self, body, x, R=None, v=None, omega=None):
+        a = [np.ascontiguousarray(q, np.float64) if q is not None else None for q in (x, R, v, omega)]
+        self.L.amo_activate_body(self.h, int(body), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]))
+
+    def remove_body(self, body):
+        self.L.amo_remove_body(self.h, int(body))
+
+    def set_mouse_spring(self, body, grab_point_b=None, point_w=None, stiffness=50.0, damping=10.0, at_com=False):
+        g = np.ascontiguousarray(grab_point_b, np.float64) if grab_point_b is not None else None
+        w = np.ascontiguousarray(point_w, np.float64) if point_w is not None else None
+        self.L.amo_set_mouse_spring(self.h, -1 if body is None else int(body), _p(g), _p(w), float(stiffness), float(damping), int(at_com))
+
+    def apply_impulse(self, body, picked_point_b, end_point_w, scale=1.0):
+        g = np.ascontiguousarray(picked_point_b, np.float64)
+        w = np.ascontiguousarray(end_point_w, np.float64)
+        self.L.amo_apply_impulse(self.h, int(body), _p(g), _p(w), float(scale))
 
     def list_order(self):
         out = np.zeros(self.n, np.int32)

@@ -71,7 +71,8 @@ def pile_with_bullet(nx=2, ny=3, nz=2, height=45.0):
     return _boxes_blob(np.ones((len(xs), 3)), xs, Rs)
 
 
-def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
+def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None, script=None):
+    """script: {step: f(system)} applied to BOTH sides before that step (UI / Factory hooks)"""
     from adaptivemerging_b200.system import RigidBodySystem
     from oracle.oracle import Oracle
     gpu = RigidBodySystem(0).load(blob, p)
@@ -82,6 +83,9 @@ def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
     worst = 0.0
     gpu.hub_contacts = 0
     for step in range(steps):
+        if script and step in script:
+            script[step](gpu)
+            script[step](cpu)
         if poke and step in poke:
             body, dv, dw = poke[step]
             gpu.add_body_velocity(body, dv, dw)
@@ -103,7 +107,10 @@ def lockstep(blob, p, steps, poke=None, tol=1e-6, options=None):
         assert np.array_equal(g["sleeping"], o["sleeping"]), f"step {step}: sleeping flags differ"
         assert np.array_equal(g["collection"] >= 0, o["collection"] >= 0), f"step {step}: merged sets differ"
         # RigidBodySystem.bodies list order (decides Contact.body1/body2 and the emission order of later steps)
-        assert np.array_equal(gpu.list_order(), np.unique(cpu.list_order(), return_inverse=True)[1]), f"step {step}: body list order differs"
+        lo = cpu.list_order()
+        inlist = lo >= 0  # (dormant bodies are in no list)
+        assert np.array_equal(np.unique(gpu.list_order(raw=True)[inlist], return_inverse=True)[1],
+                              np.unique(lo[inlist], return_inverse=True)[1]), f"step {step}: body list order differs"
     ev_g = sorted(map(tuple, gpu.events().tolist()))
     ev_o = sorted(map(tuple, cpu.events().tolist()))
     return gpu, cpu, ev_g, ev_o, worst
