@@ -269,8 +269,10 @@ static void stepOnce(am3d_ctx* c, double dt) {
   c->T.unmerging = evMs(c, 14, 4) * 1e-3;
   c->T.lcp_solve = evMs(c, 4, 5) * 1e-3;
   c->T.merging = evMs(c, 6, 15) * 1e-3;
-  c->T.merging_build = c->T.merging;
-  c->T.unmerging_build = c->T.unmerging;
+  // Merging.params.mergingBuildTime / unmergingBuildTime: the part after the merge / unmerge conditions were evaluated
+  c->T.merging_build = c->mergeBuildTimed ? evMs(c, 22, 15) * 1e-3 : 0.0;
+  c->T.unmerging_build = c->unmergeBuildTimed ? evMs(c, 23, 4) * 1e-3 : 0.0;
+  c->mergeBuildTimed = c->unmergeBuildTimed = false;
   c->T.compute_time = evMs(c, 0, 7) * 1e-3;
   c->T.n_bodies = NB - c->nDormant - c->nMergedLeaves + c->nCollections;  // bodies.size(): a collection counts as one (RigidBodySystem.java:503)
   c->T.n_contacts = c->cur.n;  // collision.contacts.size() at the end of the step, unmerge-appended contacts included

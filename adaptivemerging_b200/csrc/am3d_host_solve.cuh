@@ -390,6 +390,8 @@ static void mergeStep(am3d_ctx* c) {
          c->bp.nState.p, MP, c->mflag.p, c->uf.p, c->counters.p + 4);
   int nFlagged = readInt(c, c->counters.p + 4);
   if (nFlagged == 0) return;
+  CK(cudaEventRecord(c->ev[22], c->stream));  // everything after the conditions = building collections (Merging.java mergingBuildTime)
+  c->mergeBuildTimed = true;
   c->mergingEvent = true;
   LAUNCH(c, k_uf_flatten, nblk(ns), BLK, ns, c->uf.p);
   c->compEnt.ensure(ns + 2); c->compBest.ensure(ns + 2); c->needNew.ensure(ns + 2); c->newScan.ensure(ns + 2); c->target.ensure(ns + 2);
@@ -471,6 +473,8 @@ static bool unmergeStep(am3d_ctx* c) {
          P.unmerge_normal, P.unmerge_friction, c->ibp.nMetric.p, c->ibpCut.p, c->collCuts.p, c->counters.p + 5);
   int nCuts = readInt(c, c->counters.p + 5);
   if (nCuts == 0) return false;
+  CK(cudaEventRecord(c->ev[23], c->stream));  // unmergingBuildTime: splitting the collections
+  c->unmergeBuildTimed = true;
   c->uf.ensure(ns + 1);
   LAUNCH(c, k_uf_init, nblk(nb), BLK, nb, c->uf.p);
   LAUNCH(c, k_unm_union, nblk(nib), BLK, nib, c->ibp.alive.p, c->ibpCut.p, c->ibp.b1.p, c->ibp.b2.p, c->parent.p, c->collCuts.p, nb, c->uf.p);

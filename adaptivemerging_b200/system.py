@@ -15,6 +15,7 @@ import numpy as np
 
 from . import _capi
 from .ctypes_defs import (BPC_DTYPE, CONTACT_DTYPE, am3d_params, am3d_timings, apply_overrides, default_params)
+from .csvlog import CsvLog
 from .scene import SceneBlob, load_xml
 
 
@@ -41,6 +42,9 @@ class RigidBodySystem:
         self.mergingTime = 0.0
         self.unmergingTime = 0.0
         self.warmStartTime = 0.0
+        self.saveCSV = False        # RigidBodySystem.saveCSV (:547): one CSV row per advanceTime, exportDataToFile :495-542
+        self.sceneName = "scene"
+        self._csv = CsvLog()
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _ck(self, rc):
@@ -49,6 +53,8 @@ class RigidBodySystem:
             raise _capi.Am3dError(rc, msg.decode() if msg else "")
 
     def close(self):
+        if getattr(self, "_csv", None):
+            self._csv.close()
         if getattr(self, "_h", None):
             self._L.am3d_destroy(self._h)
             self._h = None
@@ -88,6 +94,8 @@ class RigidBodySystem:
         self.mergingTime = t.merging
         self.unmergingTime = t.unmerging
         self.warmStartTime = t.warmstart
+        if self.saveCSV or self._csv.stream is not None:
+            self._csv.export(self.saveCSV, self.sceneName, bool(self.params.enable_merging), t)
 
     def step_async(self, dt, nsteps=1):
         """hand nsteps to the context's worker thread and return (am3d_step_async); sync() waits"""
