@@ -377,6 +377,7 @@ int am3d_create(int device, am3d_ctx** out) {
       CK(cudaFuncSetAttribute(k_pgs_giant<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_layers, 256, 0)); c->bfsBlocks = coop ? sms * perSm : 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_color_coop, 256, 0)); c->colorBlocks = coop ? sms * perSm : 0;
     if (const char* e = getenv("AM3D_PGS_PERSISTENT")) c->usePersistent = atoi(e);
     if (const char* e = getenv("AM3D_GIANT_WARPS")) c->useGiantWarps = atoi(e);
     if (const char* e = getenv("AM3D_GIANT_CHUNK")) c->giantChunk = atoi(e);

@@ -240,7 +240,8 @@ struct am3d_ctx {
   int giantChunk = 512;   // am3d_set_option("giant_chunk", n): 0 = never split a pair
   int nPairsSolve = 0;    // body pairs of the last solve (nGroups counts chunks)
   int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list
-  int bfsBlocks = 0;
+  int bfsBlocks = 0, colorBlocks = 0;
+  DevBuf<int> colorCtl;
   bool orderingTimed = false, mergeBuildTimed = false, unmergeBuildTimed = false;
   std::vector<int> events;  // (step, kind, bodyLo, bodyHi) quadruples
   bool recordEvents = true; // am3d_set_option("record_events", 0): long batched runs (one device->host copy per merge step saved)

@@ -145,7 +145,7 @@ static void warmStart(am3d_ctx* c, bool postStab = false) {
   }
   WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,
             c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
-            c->prev.n, c->prev.nSorted, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, postStab ? c->prev.prevViol.p : c->prev.viol.p, c->prev.lam.p,
+            c->prev.n, c->prev.nSorted, c->cur.n, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, postStab ? c->prev.prevViol.p : c->prev.viol.p, c->prev.lam.p,
             useIdx, c->wsK0s.p, c->wsK1s.p, c->wsIdx.p,
             c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
   LAUNCH(c, k_warm_start_plain, nblk(c->cur.n), BLK, c->cur.n, W);

@@ -188,6 +188,7 @@ static void resetState(am3d_ctx* c) {
     h2dv(c, c->spBodies, bodies); h2dv(c, c->spBodyStart, start); h2dv(c, c->spBodyList, list);
   }
   c->counters.ensure(64); c->counters.zero(64, c->stream);
+  c->colorCtl.ensure(8);
   c->iterState.ensure(8); c->iterState.zero(8, c->stream);
   c->cur.n = 0; c->prev.n = 0; c->bp.n = 0; c->bpPrev.n = 0; c->cur.nSorted = 0; c->prev.nSorted = 0;
   {

@@ -31,24 +31,24 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
   int page = 0;
   const int maxPages = 64;
-  while (true) {
-    int remaining = 1, rounds = 0;
-    while (remaining > 0) {
-      for (int r = 0; r < 4; r++) {  // a few rounds per host read-back
-        CK(cudaMemsetAsync(c->counters.p + 2, 0, sizeof(int), c->stream));
-        LAUNCH(c, k_color_bid, nblk(ng), BLK, ng, c->grpSb1.p, c->grpSb2.p, c->grpHubMask.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p);
-        LAUNCH(c, k_color_assign, nblk(ng), BLK, ng, page, c->grpSb1.p, c->grpSb2.p, c->grpHubMask.p, c->grpPrio.p, c->grpColor.p, c->bodyBest.p,
-               c->bodyMask.p, c->counters.p + 2, c->counters.p + 3);
-      }
-      remaining = readInt(c, c->counters.p + 2);
-      if (++rounds > 100000) throw AmError(AM3D_ECUDA, "colouring did not converge");
-    }
-    int deferred = readInt(c, c->counters.p + 3);
-    if (deferred == 0) break;
-    if (++page >= maxPages) throw AmError(AM3D_ECAPACITY, "more than 4096 colours needed");
-    CK(cudaMemsetAsync(c->counters.p + 3, 0, sizeof(int), c->stream));
-    CK(cudaMemsetAsync(c->bodyMask.p, 0, c->NS * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, k_color_next_page, nblk(ng), BLK, ng, page - 1, c->grpColor.p);
+  if (c->colorBlocks <= 0) throw AmError(AM3D_ECUDA, "cooperative launch unsupported");
+  {  // the rounds run on the device (one cooperative launch, no read-back per round)
+    CK(cudaMemsetAsync(c->colorCtl.p, 0, 8 * sizeof(int), c->stream));
+    int ngv = ng, nsv = c->NS, mp = maxPages;
+    const int *s1 = c->grpSb1.p, *s2 = c->grpSb2.p, *hm = c->grpHubMask.p;
+    const unsigned long long* pr = c->grpPrio.p;
+    int* col = c->grpColor.p;
+    unsigned long long *bb = c->bodyBest.p, *bm = c->bodyMask.p;
+    int* ctl = c->colorCtl.p;
+    void* args[] = {&ngv, &nsv, &mp, &s1, &s2, &hm, &pr, &col, &bb, &bm, &ctl};
+    int blocks = std::min(c->colorBlocks, std::max(1, nblk(ng, 256)));
+    CK(cudaLaunchCooperativeKernel((const void*)k_color_coop, dim3(blocks), dim3(256), args, 0, c->stream));
+    c->kernelLaunches++;
+    int out[2];
+    CK(cudaMemcpyAsync(out, c->colorCtl.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (out[1]) throw AmError(AM3D_ECAPACITY, "more than 4096 colours needed");
+    page = out[0] - 1;
   }
   int maxColors = (page + 1) * 64;
   int endBit = 20 + (layer ? layerBits : 0);

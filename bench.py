@@ -203,10 +203,12 @@ def run_leg(local, blob, params, steps, warmup, settle, with_e2e, barrier):
     t0 = time.perf_counter()
     np_bytes = np_s = 0.0
     sum_contacts = 0
+    series = []
     for _ in range(steps):
         sysm.advanceTime(0.05)
         t = sysm.timings()
         sum_contacts += t.n_contacts
+        series.append(round(t.compute_time * 1e3, 2))
         # narrowphase, SURVEY.md 8d: 8 B + 2 x 96 B per candidate pair, 80 B per emitted contact
         np_bytes += 200.0 * t.n_pairs + 80.0 * t.n_contacts
         np_s += t.narrowphase_kernel_time
@@ -221,7 +223,7 @@ def run_leg(local, blob, params, steps, warmup, settle, with_e2e, barrier):
     tm = sysm.timings()
     out = {"ms": ms, "wall": wall, "clocks": clk, "np_bytes": np_bytes, "np_s": np_s, "sum_contacts": sum_contacts,
            "row_updates": s1["row_updates"] - s0["row_updates"], "solve_s": s1["solve_seconds"] - s0["solve_seconds"],
-           "launches": s1["kernel_launches"] - s0["kernel_launches"], "solve_launches": s1["solve_launches"] - s0["solve_launches"],
+           "series": series, "launches": s1["kernel_launches"] - s0["kernel_launches"], "solve_launches": s1["solve_launches"] - s0["solve_launches"],
            "tm": {"n_collections": tm.n_collections, "n_contacts": tm.n_contacts, "n_pairs": tm.n_pairs, "pgs_colors": tm.pgs_colors,
                   "n_bodies_top_level": tm.n_bodies,
                   "phase_ms": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "update_collections": tm.update_collections * 1e3,
@@ -307,14 +309,14 @@ def main():
     ap.add_argument("--y0", type=float, default=None, help="funnel: height of the lowest lattice layer (SURVEY.md: 110)")
     ap.add_argument("--settle", type=int, default=-1,
                     help="untimed steps before the warm-up so that the workload is in its loaded phase "
-                         "(default: 150 batch = towers collapsing onto the platform, 20 stack/pile, 35 funnel = second layer "
+                         "(default: 120 batch = towers collapsing onto the platform with the first collections formed, 20 stack/pile, 35 funnel = second layer "
                          "landing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short config M / config F legs reported under `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.settle < 0:
-        args.settle = {"batch": 150, "stack": 20, "pile": 20, "funnel": 35}[args.workload]
+        args.settle = {"batch": 120, "stack": 20, "pile": 20, "funnel": 35}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -383,7 +385,7 @@ def main():
         "pgs_row_updates_vs_baseline": (float(tot[1]) / max(float(counts[2]), 1e-12)) / 23.4e6,
         "collections_last_step": tm["n_collections"], "contacts_last_step": tm["n_contacts"], "pairs_last_step": tm["n_pairs"],
         "pgs_phases": tm["pgs_colors"], "phase_ms_last_step": tm["phase_ms"],
-        "wall_ms_per_step": 1e3 * leg["wall"] / args.steps,
+        "wall_ms_per_step": 1e3 * leg["wall"] / args.steps, "step_ms_series": leg["series"],
         "roofline": roofline_of(leg, args.workload, args.steps),
         "roofline_narrowphase": narrow_roofline_of(leg, args.steps),
     }

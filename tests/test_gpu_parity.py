@@ -40,6 +40,75 @@ def test_contact_sets_bit_exact_teacher_forced(scene):
     assert checked > 50
 
 
+@pytest.mark.parametrize("scene", ["torsos", "funnel"])
+def test_contact_sets_bit_exact_teacher_forced_trees_and_composites(scene):
+    """the same for sphere trees against the plane / each other (torso_flux.sph meshes) and for composite parts against
+    trees and boxes (funnel.xml): identity incl. leaf ids and part indices, world points, normals, depths, bit for bit"""
+    from adaptivemerging_b200.ctypes_defs import apply_overrides
+    from adaptivemerging_b200.scene import funnel_pile
+    from tests.util import golden_scene
+    if scene == "torsos":
+        blob, steps, every = golden_scene("torsos"), 90, 6
+    else:
+        blob, steps, every = funnel_pile(golden_scene("funnel_template"), nx=3, ny=2, nz=3, pitch=6.0, y0=52.0), 150, 10
+    from adaptivemerging_b200.system import RigidBodySystem
+    from oracle.oracle import Oracle
+    p = apply_overrides(params(enable_merging=0), blob.overrides)
+    p.enable_merging = 0
+    gpu, cpu = RigidBodySystem(0).load(blob, p), Oracle(blob, p)
+    checked = 0
+    for step in range(steps):
+        cpu.step(0.05)
+        if step % every != every - 1:
+            continue
+        b = cpu.bodies()
+        gpu.upload_bodies(b["x"], b["R"], b["v"], b["omega"])
+        ng, no = gpu.detect(), cpu.detect()
+        assert ng == no
+        if no:
+            assert_contact_sets_equal(gpu.contacts(), cpu.contacts())
+            checked += no
+    assert checked > 200
+
+
+def test_hub_solve_residuals_against_the_reference_order():
+    """Hub bodies are the one place where the GPU's sequence is not a permutation of the reference's (Jacobi across the
+    groups of a colour for the hub's deltaV).  Evidence that does not rest on the oracle's replay of that scheme: after
+    the same 30 iterations the LCP residuals of the hub solve are compared with those of the reference's own list-order
+    Gauss-Seidel on the same contacts."""
+    from oracle.oracle import Oracle
+    from tests.util import hub_scene
+    blob = hub_scene()
+    gpu, cpu = _pair(blob, enable_merging=0)
+    ref = Oracle(blob, params(enable_merging=0))
+    gpu.set_option("hub_min_degree", 8)
+    gpu.record_orders(True)
+    for _ in range(40):
+        cpu.step(0.05)
+        ref.step(0.05)
+    b = cpu.bodies()
+    gpu.upload_bodies(b["x"], b["R"], b["v"], b["omega"])
+    assert gpu.detect() == cpu.detect() == ref.detect() > 0
+    gpu.solve(0.05)
+    order = gpu.order(0)
+    assert (order["hub_mask"] != 0).sum() > 30
+    cpu.apply_external_forces()
+    assert cpu.solve(0.05, order) == 0
+    cg, co = gpu.contacts(), cpu.contacts()
+    ko = key_index(co)
+    io = np.array([ko[k][0] for k in map(tuple, np.stack([cg[f] for f in ("body1", "body2", "csb1", "csb2", "bv1", "bv2", "info", "leaf")], 1).tolist())])
+    assert np.array_equal(cg["lambda"], co["lambda"][io])           # the oracle holds the GPU's hub solution
+    ref.apply_external_forces()
+    ref.solve(0.05)
+    r_gpu, r_ref = cpu.residuals(), ref.residuals()
+    print(f"\nhub solve, {int(r_gpu[3])} contacts: GPU normal {r_gpu[0]:.3e} cone {r_gpu[1]:.3e} tangential {r_gpu[2]:.3e} | reference order "
+          f"normal {r_ref[0]:.3e} cone {r_ref[1]:.3e} tangential {r_ref[2]:.3e}")
+    assert r_gpu[1] <= 1e-12 and r_ref[1] <= 1e-12
+    assert r_gpu[0] <= max(5 * r_ref[0], 2e-3) and r_gpu[2] <= max(5 * r_ref[2], 2e-3)
+    # and the two solutions are the same physical answer
+    assert np.abs(cpu.deltav() - ref.deltav()).max() < 5e-3
+
+
 @pytest.mark.parametrize("hub_min", [64, 2])
 def test_pgs_bit_exact_in_colour_order(hub_min):
     """hub_min = 2 forces the hub path (bodies touched by >= 2 body pairs are solved Jacobi-style across a colour,
