@@ -207,7 +207,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
   }
   CK(cudaEventRecord(c->ev[14], c->stream));
   // accumulateForUnmerging + unmerge (:135-136)
-  if (c->nCollections > 0) unmergeStep(c);
+  if (c->nCollections > 0) unmergeStep(c, dt);
   if (c->mergingEvent) {                        // sticky flag (:138-142): clear + re-apply forces on top-level bodies
     LAUNCH(c, k_reclear_top, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->mass.p, c->force.p, c->torque.p, c->dv.p,
            P.use_gravity, gx, gy);
@@ -237,7 +237,7 @@ static void stepOnce(am3d_ctx* c, double dt) {
     LAUNCH(c, k_bpc_accumulate, nblk(nbp, 128), 128, nbp, c->bp.b1.p, c->bp.b2.p, c->bp.start.p, c->bp.count.p, c->bp.nActive.p,
            c->bp.alive.p, c->cur.lam.p, c->cur.state.p, c->parent.p, c->flags.p, c->x.p, c->R.p, c->v.p, c->w.p, c->bbB.p,
            c->bbCount.p, c->bp.metricHist.p, c->bp.stateHist.p, c->bp.nMetric.p, c->bp.nState.p, P.step_accum_merging,
-           c->hasExt.p);                                                                         // (:158)
+           c->hasExt.p, P.metric_position_level ? dt : 0.0);                                     // (:158)
   }
   LAUNCH(c, k_advance_positions, nblk(NS), BLK, NS, NB, c->collAlive.p, c->parent.p, c->flags.p, c->x.p, c->R.p, c->v.p,
          c->w.p, 3, c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p, dt);                                // (:160)
@@ -307,10 +307,10 @@ static void waitPending(am3d_ctx* c) {
   }
 
 static void checkParams(const am3d_params* p) {
-  if (p->shuffle) throw AmError(AM3D_EUNSUPPORTED, "shuffle is not supported");
+  // shuffle (Collections.shuffle with an unseeded Random, CollisionProcessor.java:674): asks for an unspecified order of the
+  // Gauss-Seidel sweep; the colour order already is one (and stays deterministic), so the flag is accepted as it is
   if (p->collection_cd != 0) throw AmError(AM3D_EUNSUPPORTED, "only the brute-force collection collision mode is supported");
   if (p->merge_cycle_condition) throw AmError(AM3D_EUNSUPPORTED, "cycle merge condition is not supported");
-  if (p->metric_position_level) throw AmError(AM3D_EUNSUPPORTED, "position-level metric is not supported");
   if (p->iterations < 1 || p->iterations_in_collection < 1) throw AmError(AM3D_EINVAL, "iterations must be >= 1");
   if (p->step_accum_merging > 4 || p->step_accum_unmerging > 4 || p->step_accum_merging < 0) throw AmError(AM3D_EUNSUPPORTED, "accumulation windows above 4 steps are not supported");
   if (p->sleep_step_accum > 10 || p->sleep_step_accum < 0) throw AmError(AM3D_EUNSUPPORTED, "sleep accumulation above 10 steps is not supported");

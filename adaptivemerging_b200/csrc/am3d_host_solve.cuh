@@ -457,7 +457,7 @@ static void mergeStep(am3d_ctx* c) {
 }
 
 // Merging.unmerge (Merging.java:215-273); returns true if anything was split
-static bool unmergeStep(am3d_ctx* c) {
+static bool unmergeStep(am3d_ctx* c, double dt) {
   const am3d_params& P = c->P;
   if (!P.enable_unmerging) return false;
   if (!P.unmerge_relative_motion && !P.unmerge_normal && !P.unmerge_friction) return false;
@@ -470,7 +470,7 @@ static bool unmergeStep(am3d_ctx* c) {
   CK(cudaMemsetAsync(c->counters.p + 5, 0, sizeof(int), c->stream));
   LAUNCH(c, k_unm_flag, nblk(nib, 128), 128, nib, c->ibp.alive.p, c->ibp.b1.p, c->ibp.b2.p, c->ibp.start.p, c->ibp.count.p, c->icon.state.p,
          c->parent.p, c->flags.p, c->x.p, c->R.p, c->v.p, c->w.p, c->bbB.p, c->bbCount.p, nb, P.threshold_unmerge, P.step_accum_unmerging,
-         P.unmerge_normal, P.unmerge_friction, c->ibp.nMetric.p, c->ibpCut.p, c->collCuts.p, c->counters.p + 5);
+         P.unmerge_normal, P.unmerge_friction, P.metric_position_level ? dt : 0.0, c->ibp.nMetric.p, c->ibpCut.p, c->collCuts.p, c->counters.p + 5);
   int nCuts = readInt(c, c->counters.p + 5);
   if (nCuts == 0) return false;
   CK(cudaEventRecord(c->ev[23], c->stream));  // unmergingBuildTime: splitting the collections

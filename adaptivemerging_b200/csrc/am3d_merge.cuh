@@ -533,7 +533,7 @@ __global__ void k_unm_flag(int nib, const int* __restrict__ ialive, const int* _
                            const int* __restrict__ parent, const int* __restrict__ flags, const double* __restrict__ x,
                            const double* __restrict__ R, const double* __restrict__ v, const double* __restrict__ w,
                            const double* __restrict__ bbB, const int* __restrict__ bbCount, int nb, double thrUnmerge,
-                           int accumUnmerge, int unmNormal, int unmFriction, int* __restrict__ inMetric, int* __restrict__ icut,
+                           int accumUnmerge, int unmNormal, int unmFriction, double posDt, int* __restrict__ inMetric, int* __restrict__ icut,
                            int* __restrict__ collCuts, int* __restrict__ total) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nib) return;
@@ -543,7 +543,7 @@ __global__ void k_unm_flag(int nib, const int* __restrict__ ialive, const int* _
   int p = parent[l1];
   if (p < 0 || p != parent[l2]) return;
   if (flags[p] & AM3D_F_SLEEPING) return;
-  double metric = pairMetric(l1, l2, flags, x, R, v, w, bbB, bbCount);
+  double metric = pairMetric(l1, l2, flags, x, R, v, w, bbB, bbCount, posDt);
   int nm = inMetric[b];
   if (metric > thrUnmerge) { if (nm < 1000000) nm++; } else nm = 0;
   inMetric[b] = nm;

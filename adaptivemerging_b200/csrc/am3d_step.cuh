@@ -540,10 +540,62 @@ __device__ __forceinline__ double bodyMetric(int b, const double* x, const doubl
   }
   return largest;
 }
+// RigidBody.advancePositions :427-441 on a copy of the pose (expRodrigues :382-401, Matrix3d.normalizeCP)
+__device__ __forceinline__ xf advancedPose(const xf& T, const d3& vv, const d3& om, double dt) {
+  xf A;
+  A.t = vscaleAdd(dt, vv, T.t);
+  A.R = T.R;
+  double t = vlen(om) * dt;
+  if (t > 1e-8) {
+    d3 wn = vnormalize(om);
+    double c = cos(t), s = sin(t);
+    double c1 = 1 - c;
+    m3 dR;
+    dR.m[0] = c + wn.x * wn.x * c1;
+    dR.m[3] = wn.z * s + wn.x * wn.y * c1;
+    dR.m[6] = -wn.y * s + wn.x * wn.z * c1;
+    dR.m[1] = -wn.z * s + wn.x * wn.y * c1;
+    dR.m[4] = c + wn.y * wn.y * c1;
+    dR.m[7] = wn.x * s + wn.y * wn.z * c1;
+    dR.m[2] = wn.y * s + wn.x * wn.z * c1;
+    dR.m[5] = -wn.x * s + wn.y * wn.z * c1;
+    dR.m[8] = c + wn.z * wn.z * c1;
+    dR = mmul(dR, T.R);
+    A.R = mnormalizeCP(dR);
+  }
+  return A;
+}
+// metricPositionLevel (MotionMetricProcessor.java:75-116): how far the bounding-box points of each body move in the
+// other body's frame over one position update, divided by dt
+__device__ __forceinline__ double pairMetricPos(int a, int b, const double* x, const double* R, const double* v, const double* w,
+                                                const double* bbB, const int* bbCount, double dt) {
+  xf T1, T2;
+  T1.R = ldm(R + 9 * a); T1.t = ld3(x + 3 * a);
+  T2.R = ldm(R + 9 * b); T2.t = ld3(x + 3 * b);
+  xf A1 = advancedPose(T1, ld3(v + 3 * a), ld3(w + 3 * a), dt), A2 = advancedPose(T2, ld3(v + 3 * b), ld3(w + 3 * b), dt);
+  double largest = 0, inv = 1. / dt;
+  int n = bbCount[a];
+  for (int k = 0; k < n; k++) {
+    d3 point = ld3(bbB + 24 * a + 3 * k);
+    d3 pB = xfInvP(T2, xfP(T1, point));
+    pB = xfInvP(A1, xfP(A2, pB));
+    largest = fmax(vlen(vscale(inv, vsub(point, pB))), largest);
+  }
+  n = bbCount[b];
+  for (int k = 0; k < n; k++) {
+    d3 point = ld3(bbB + 24 * b + 3 * k);
+    d3 pB = xfInvP(T1, xfP(T2, point));
+    pB = xfInvP(A2, xfP(A1, pB));
+    largest = fmax(vlen(vscale(inv, vsub(point, pB))), largest);
+  }
+  return largest;
+}
 __device__ __forceinline__ double pairMetric(int a, int b, const int* flags, const double* x, const double* R,
-                                             const double* v, const double* w, const double* bbB, const int* bbCount) {
+                                             const double* v, const double* w, const double* bbB, const int* bbCount,
+                                             double posDt = 0.0 /* > 0: metric at position level */) {
   if (flags[a] & AM3D_F_PINNED) return bodyMetric(b, x, R, v, w, bbB, bbCount);
   if (flags[b] & AM3D_F_PINNED) return bodyMetric(a, x, R, v, w, bbB, bbCount);
+  if (posDt > 0.0) return pairMetricPos(a, b, x, R, v, w, bbB, bbCount, posDt);
   double largest = 0;
   for (int i = 0; i < 2; i++) {
     int body = i == 0 ? a : b;
@@ -1599,14 +1651,14 @@ __global__ void k_bpc_accumulate(int nbp, const int* __restrict__ bb1, const int
                                  const int* __restrict__ flags, const double* __restrict__ x, const double* __restrict__ R,
                                  const double* __restrict__ v, const double* __restrict__ w, const double* __restrict__ bbB,
                                  const int* __restrict__ bbCount, double* __restrict__ mh, int* __restrict__ sh,
-                                 int* __restrict__ nm, int* __restrict__ nst, int accum, int* __restrict__ hasExt) {
+                                 int* __restrict__ nm, int* __restrict__ nst, int accum, int* __restrict__ hasExt, double posDt) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nbp) return;
   if (nActive[b] == 0) { alive[b] = 0; return; }  // removeEmptyBodyPairContacts :191-208
   int l1 = bb1[b], l2 = bb2[b];
   int a = parent[l1] >= 0 ? parent[l1] : l1, c = parent[l2] >= 0 ? parent[l2] : l2;
   if (accum > 4) accum = 4;
-  double m = pairMetric(a, c, flags, x, R, v, w, bbB, bbCount);
+  double m = pairMetric(a, c, flags, x, R, v, w, bbB, bbCount, posDt);
   int n = nm[b];
   if (n < 4) mh[4 * b + n++] = m;
   else { for (int k = 0; k < 3; k++) mh[4 * b + k] = mh[4 * b + k + 1]; mh[4 * b + 3] = m; }

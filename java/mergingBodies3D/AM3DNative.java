@@ -51,6 +51,16 @@ final class AM3DNative implements AutoCloseable {
     private static final MethodHandle ADD_BODY_VELOCITY = h("am3d_add_body_velocity",
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle ADD_VELOCITIES = h("am3d_add_velocities", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    // callers' hooks (SURVEY.md 8f.2): Factory / add / remove, mouse tools, Animation, list order, async stepping
+    private static final MethodHandle ACTIVATE_BODY = h("am3d_activate_body", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle REMOVE_BODY = h("am3d_remove_body", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+    private static final MethodHandle SET_MOUSE_SPRING = h("am3d_set_mouse_spring",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT));
+    private static final MethodHandle APPLY_IMPULSE = h("am3d_apply_impulse", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_DOUBLE));
+    private static final MethodHandle SET_BODY_SLEEPING = h("am3d_set_body_sleeping", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle LIST_ORDER = h("am3d_download_list_order", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
+    private static final MethodHandle STEP_ASYNC = h("am3d_step_async", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT));
+    private static final MethodHandle SYNC = h("am3d_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS));
 
     /** sizeof(am3d_params), sizeof(am3d_timings), sizeof(am3d_contact): see the struct definitions in am3d.h */
     static final long SIZEOF_PARAMS = 264, SIZEOF_TIMINGS = 128, SIZEOF_CONTACT = 264;
@@ -109,6 +119,19 @@ final class AM3DNative implements AutoCloseable {
     void setBodyVelocity(int body, MemorySegment v3, MemorySegment w3) { try { check((int) SET_BODY_VELOCITY.invokeExact(ctx, body, v3, w3)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     void addBodyVelocity(int body, MemorySegment dv3, MemorySegment dw3) { try { check((int) ADD_BODY_VELOCITY.invokeExact(ctx, body, dv3, dw3)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     void addVelocities(MemorySegment dv, MemorySegment dw) { try { check((int) ADD_VELOCITIES.invokeExact(ctx, dv, dw)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+
+    /** Factory.generateBody (Factory.java:99-116): a dormant clone (body_flags bit 16 in the scene blob) enters system.bodies */
+    void activateBody(int body, MemorySegment x3, MemorySegment R9, MemorySegment v3, MemorySegment w3) { try { check((int) ACTIVATE_BODY.invokeExact(ctx, body, x3, R9, v3, w3)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void removeBody(int body) { try { check((int) REMOVE_BODY.invokeExact(ctx, body)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    /** MouseSpringForce.setPicked + the stiffness / damping parameters; body = -1 releases */
+    void setMouseSpring(int body, MemorySegment grabPointB, MemorySegment pointW, double k, double c, boolean atCOM) { try { check((int) SET_MOUSE_SPRING.invokeExact(ctx, body, grabPointB, pointW, k, c, atCOM ? 1 : 0)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    /** MouseImpulse.release(): applied inside the next step */
+    void applyImpulse(int body, MemorySegment pickedPointB, MemorySegment endPointW, double scale) { try { check((int) APPLY_IMPULSE.invokeExact(ctx, body, pickedPointB, endPointW, scale)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void setBodySleeping(int body, boolean sleeping) { try { check((int) SET_BODY_SLEEPING.invokeExact(ctx, body, sleeping ? 1 : 0)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    /** monotone position keys of every leaf's top-level entity: sort by them to rebuild system.bodies in the reference's order */
+    void listOrder(MemorySegment int64PerBody) { try { check((int) LIST_ORDER.invokeExact(ctx, int64PerBody)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void stepAsync(double dt, int n) { try { check((int) STEP_ASYNC.invokeExact(ctx, dt, n)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    void sync() { try { check((int) SYNC.invokeExact(ctx)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
 
     @Override public void close() {
         try { int rc = (int) DESTROY.invokeExact(ctx); } catch (Throwable ignored) { }

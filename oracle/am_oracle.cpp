@@ -1217,9 +1217,39 @@ struct System {
     }
     return largest;
   }
-  static double pairMetric(const Body* body1, const Body* body2) {
+  // MotionMetricProcessor.getLargestVelocityNorm(body1, body2, dt) :75-116 (metricPositionLevel)
+  static double largestVelocityNormPos(const Body* body1, const Body* body2, double dt) {
+    double largest = 0;
+    Body a1, a2;  // body1Advanced.set(body1); advancePositions(dt)
+    a1.x = body1->x; a1.theta = body1->theta; a1.v = body1->v; a1.omega = body1->omega;
+    a1.massAngular0 = body1->massAngular0; a1.jinv0 = body1->jinv0;
+    advancePositionsBase(&a1, dt);
+    a2.x = body2->x; a2.theta = body2->theta; a2.v = body2->v; a2.omega = body2->omega;
+    a2.massAngular0 = body2->massAngular0; a2.jinv0 = body2->jinv0;
+    advancePositionsBase(&a2, dt);
+    Xf T1 = body1->B2W(), T2 = body2->B2W(), A1 = a1.B2W(), A2 = a2.B2W();
+    for (const V3& point : body1->boundingBoxB) {
+      V3 pW = T1.transformP(point);
+      V3 pB = T2.inverseTransformP(pW);
+      pW = A2.transformP(pB);
+      pB = A1.inverseTransformP(pW);
+      V3 v1 = scale(1. / dt, sub(point, pB));
+      largest = std::max(length(v1), largest);
+    }
+    for (const V3& point : body2->boundingBoxB) {
+      V3 pW = T2.transformP(point);
+      V3 pB = T1.inverseTransformP(pW);
+      pW = A1.transformP(pB);
+      pB = A2.inverseTransformP(pW);
+      V3 v2 = scale(1. / dt, sub(point, pB));
+      largest = std::max(length(v2), largest);
+    }
+    return largest;
+  }
+  double pairMetric(const Body* body1, const Body* body2) {
     if (body1->pinned) return largestVelocityNorm1(body2);
     if (body2->pinned) return largestVelocityNorm1(body1);
+    if (P.metric_position_level) return largestVelocityNormPos(body1, body2, curDt);  // BodyPairContact.java:92-93, :134-135
     return largestVelocityNorm2(body1, body2);
   }
   // accumulateForMerging :83-121

@@ -30,8 +30,7 @@ def test_call_order_and_bad_arguments():
     s.close()
 
 
-@pytest.mark.parametrize("field", ["shuffle", "merge_cycle_condition",
-                                   "metric_position_level", "collection_cd"])
+@pytest.mark.parametrize("field", ["merge_cycle_condition", "collection_cd"])
 def test_unsupported_reference_options_are_refused(field):
     s = RigidBodySystem(0)
     p = default_params()
