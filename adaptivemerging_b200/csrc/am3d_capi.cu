@@ -191,7 +191,8 @@ static void stepOnce(am3d_ctx* c, double dt) {
   CK(cudaEventRecord(c->ev[3], c->stream));
   if (P.enable_sleeping) {                      // sleeping.wake() (:128)
     LAUNCH(c, k_wake_pairs, nblk(c->bp.n), BLK, c->bp.n, c->bp.b1.p, c->bp.b2.p, c->parent.p, c->flags.p, c->metricCount.p);
-    LAUNCH(c, k_wake_springs, nblk(c->NSP), BLK, c->NSP, c->spType.p, c->spB1.p, c->spB2.p, c->parent.p, c->flags.p, c->metricCount.p);
+    if (c->nBodyBodySprings > 0)
+      LAUNCH(c, k_wake_springs, nblk(c->NSP), BLK, c->NSP, c->spType.p, c->spB1.p, c->spB2.p, c->parent.p, c->flags.p, c->metricCount.p);
   }
   // single sweep over external + internal contacts (:131), only while collections exist
   c->T.update_collections = c->T.contact_ordering = c->T.single_it_pgs = 0;
@@ -375,6 +376,23 @@ int am3d_create(int device, am3d_ctx** out) {
       CK(cudaFuncSetAttribute(k_pgs_giant<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
       CK(cudaFuncSetAttribute(k_pgs_giant<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
       CK(cudaFuncSetAttribute(k_pgs_giant<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gsm));
+    }
+    {  // how many 8-CTA clusters of the partitioned sweep fit the GPU at once
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(PGS_CLUSTER * sms);
+      cfg.blockDim = dim3(128);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = PGS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n1 = 0, n2 = 0;
+      if (cudaOccupancyMaxActiveClusters(&n1, k_pgs_cluster<false>, &cfg) != cudaSuccess) { n1 = 0; cudaGetLastError(); }
+      if (cudaOccupancyMaxActiveClusters(&n2, k_pgs_cluster<true>, &cfg) != cudaSuccess) { n2 = 0; cudaGetLastError(); }
+      c->maxClusters = std::min(n1, n2);
+      if (amTrace()) fprintf(stderr, "[am3d] co-resident clusters of %d CTAs: %d / %d\n", PGS_CLUSTER, n1, n2);
+      if (const char* e = getenv("AM3D_PGS_CLUSTERS")) c->useClusters = atoi(e);
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_bfs_layers, 256, 0)); c->bfsBlocks = coop ? sms * perSm : 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_color_coop, 256, 0)); c->colorBlocks = coop ? sms * perSm : 0;
@@ -851,6 +869,7 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   else if (!strcmp(name, "pgs_persistent")) c->usePersistent = (int)value;
   else if (!strcmp(name, "record_events")) c->recordEvents = value != 0;
   else if (!strcmp(name, "giant_warps")) c->useGiantWarps = (int)value;
+  else if (!strcmp(name, "pgs_clusters")) c->useClusters = (int)value;
   else if (!strcmp(name, "giant_chunk")) c->giantChunk = (int)value;
   else if (!strcmp(name, "merge_exact_max_pairs")) c->mergeExactMax = (int)value;
   else throw AmError(AM3D_EINVAL, std::string("unknown option ") + name);

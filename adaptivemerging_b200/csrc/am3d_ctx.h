@@ -180,7 +180,7 @@ struct am3d_ctx {
   DevBuf<int> spType, spB1, spB2;
   DevBuf<double> spPb1, spPb2, spPw, spK, spD, spL0, spLs;
   DevBuf<int> spBodyStart, spBodyList;  // CSR body -> (spring<<1 | side), in spring order
-  int nSpringBodies = 0;
+  int nSpringBodies = 0, nBodyBodySprings = 0;
   DevBuf<int> spBodies;
 
   // ---- broadphase ---------------------------------------------------------------------------------
@@ -239,6 +239,10 @@ struct am3d_ctx {
   DevBuf<int> chN, chFirst, cgB1, cgB2, cgCount, cgStart, cgLayer, cgLead;  // body pairs cut into chunks of giantChunk contacts
   int giantChunk = 512;   // am3d_set_option("giant_chunk", n): 0 = never split a pair
   int nPairsSolve = 0;    // body pairs of the last solve (nGroups counts chunks)
+  // partitions of batched scenes, one thread-block cluster each (k_pgs_cluster)
+  int useClusters = 1, maxClusters = 0, nPart = 0, hPartScenes = 0;
+  DevBuf<int> partRange, partSceneStart, partRemaining;
+  std::vector<int> hPartSceneStart, hPartCount;
   int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list
   int bfsBlocks = 0, colorBlocks = 0;
   DevBuf<int> colorCtl;

@@ -185,6 +185,8 @@ static void resetState(am3d_ctx* c) {
     }
     start.push_back((int)ent.size());
     c->nSpringBodies = (int)bodies.size();
+    c->nBodyBodySprings = 0;
+    for (int s = 0; s < H.nsp; s++) c->nBodyBodySprings += H.sp_type[s] == AM3D_SPRING_BODYBODY;
     h2dv(c, c->spBodies, bodies); h2dv(c, c->spBodyStart, start); h2dv(c, c->spBodyList, list);
   }
   c->counters.ensure(64); c->counters.zero(64, c->stream);

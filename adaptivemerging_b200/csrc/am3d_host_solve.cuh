@@ -17,7 +17,7 @@ static ContactPtrs contactPtrs(ContactSet& S) {
 // colour the groups (body pairs) so that no two groups of a colour share a non-pinned solver body
 // and order them by (layer, colour) phases; layer = nullptr for the full solve
 static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, const int* gcount, const int* lead, int inCollection,
-                         const int* layer, int layerBits) {
+                         const int* layer, int layerBits, bool giantsPossible) {
   c->grpColor.ensure(ng + 1); c->grpPrio.ensure(ng + 1); c->grpSb1.ensure(ng + 1); c->grpSb2.ensure(ng + 1);
   c->grpPos.ensure(ng + 1); c->grpOrder.ensure(ng + 1); c->grpKey.ensure(ng + 1); c->grpKeySorted.ensure(ng + 1); c->grpVal.ensure(ng + 1);
   c->grpDegree.ensure(c->NS + 1); c->grpHubMask.ensure(ng + 1);
@@ -53,7 +53,17 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   int maxColors = (page + 1) * 64;
   int endBit = 20 + (layer ? layerBits : 0);
   if (!layer) endBit = 8 + bitsFor((unsigned long long)maxColors);
-  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, c->grpKey.p, c->grpVal.p);
+  // many small scenes: partitions of consecutive scenes, one thread-block cluster each (k_pgs_cluster)
+  int nScenes = c->H.nscenes;
+  c->nPart = 0;
+  int partShift = 0;
+  if (c->useClusters && c->maxClusters > 0 && nScenes >= 2 * c->maxClusters && nScenes <= 64 * c->maxClusters && !giantsPossible) {
+    c->nPart = c->maxClusters;
+    partShift = endBit;
+    endBit += bitsFor((unsigned long long)c->nPart);
+  }
+  LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, gb1, c->scene.p, partShift, c->nPart, nScenes, c->grpKey.p,
+         c->grpVal.p);
   cubRun(c, [&](void* t, size_t& b) {
     return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
   });
@@ -68,6 +78,21 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   CK(cudaStreamSynchronize(c->stream));
   c->nColors = nPhases;
   c->nGroups = ng;
+  if (c->nPart > 0) {
+    c->partRange.ensure(2 * (size_t)c->nPart + 2);
+    CK(cudaMemsetAsync(c->partRange.p, 0, 2 * (size_t)c->nPart * sizeof(int), c->stream));
+    LAUNCH(c, k_part_phases, nblk(nPhases), BLK, nPhases, c->dColorStart.p, c->grpKeySorted.p, partShift, c->partRange.p);
+    if ((int)c->hPartSceneStart.size() != c->nPart + 1 || c->hPartScenes != nScenes) {  // scenes of partition p: those with s * nPart / nScenes == p
+      c->hPartSceneStart.assign(c->nPart + 1, nScenes);
+      for (int s = nScenes - 1; s >= 0; s--) c->hPartSceneStart[(long long)s * c->nPart / nScenes] = s;
+      for (int k = c->nPart - 1; k >= 0; k--) c->hPartSceneStart[k] = std::min(c->hPartSceneStart[k], c->hPartSceneStart[k + 1]);
+      c->hPartScenes = nScenes;
+      c->hPartCount.resize(c->nPart);
+      for (int k = 0; k < c->nPart; k++) c->hPartCount[k] = c->hPartSceneStart[k + 1] - c->hPartSceneStart[k];
+      c->partSceneStart.ensure(c->nPart + 2);
+      CK(cudaMemcpyAsync(c->partSceneStart.p, c->hPartSceneStart.data(), (c->nPart + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+  }
 }
 
 // One contact set taking part in a solve: its groups start at groupOffset in the group list.
@@ -138,12 +163,15 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
     layer = c->grpLayer.p;
     layerBits = 1;
   }
-  // cut pairs with hundreds of contacts into chunks (only scenes with sphere trees can have them)
+  // pairs with hundreds of contacts exist only between sphere trees with many leaves: ask the last detection
+  bool giantsPossible = false;
+  if (c->NN > 1) giantsPossible = readInt(c, c->counters.p + 8 + c->bpSlot) > 64 || (sweep && c->icon.n > 0);
+  // cut them into chunks
   const int np = ng;
   const int *pcount = gcount, *pstart = gstart;
   const int *chunkFirst = nullptr, *lead = nullptr;
   int chunkLen = 0;
-  if (c->NN > 0 && c->giantChunk > 0) {
+  if (giantsPossible && c->giantChunk > 0) {
     c->chN.ensure(np + 2); c->chFirst.ensure(np + 2);
     LAUNCH(c, k_chunk_count, nblk(np), BLK, np, pcount, c->giantChunk, c->chN.p);
     int total = scanTotal(c, c->chN, c->chFirst, np);
@@ -159,7 +187,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
     }
   }
   c->nPairsSolve = np;
-  colourGroups(c, ng, gb1, gb2, gcount, lead, sweep ? 1 : 0, layer, layerBits);
+  colourGroups(c, ng, gb1, gb2, gcount, lead, sweep ? 1 : 0, layer, layerBits, giantsPossible);
   c->sgB1.ensure(ng + 1); c->sgB2.ensure(ng + 1); c->sgStart.ensure(ng + 2); c->sgCount.ensure(ng + 2); c->sgFlags.ensure(ng + 1);
   c->sgBpc.ensure(ng + 1); c->sgMass.ensure(20 * (size_t)ng + 20); c->sgMu.ensure(ng + 1); c->sgScene.ensure(ng + 1);
   int nScenes = c->H.nscenes;
@@ -218,14 +246,13 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   // giant groups (sphere-tree pairs with hundreds of contacts) lead their phases and are solved one warp each
   std::vector<int> giants(c->nColors, 0);
   int nGiants = 0;
-  {
+  if (giantsPossible && c->useGiantWarps) {
     c->phaseGiants.ensure(c->nColors + 1);
     CK(cudaMemsetAsync(c->phaseGiants.p, 0, (c->nColors + 1) * sizeof(int), c->stream));
     LAUNCH(c, k_phase_giants, nblk(ng), BLK, ng, c->sgCount.p, c->sgPhase.p, c->phaseGiants.p);
     CK(cudaMemcpyAsync(giants.data(), c->phaseGiants.p, c->nColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     for (int g : giants) nGiants += g;
-    if (!c->useGiantWarps) { std::fill(giants.begin(), giants.end(), 0); nGiants = 0; }
   }
   // iterState: [1] every scene done, [2] largest iteration count, [4] contact-iterations, [6] scenes still iterating
   unsigned long long is0[8] = {0, 0, 0, 0, 0, 0, (unsigned long long)nScenes, 0};
@@ -238,7 +265,33 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   // launch per colour (no barrier cost, full occupancy per launch)
   long long avgGroups = ng / std::max(1, c->nColors);
   bool persistent = nGiants == 0 && c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
-  if (persistent) {
+  if (c->nPart > 0 && nGiants == 0) {
+    bool hubs = c->nHubRuns > 0;
+    if (hubs) {
+      c->dColorRunStart.ensure(c->colorRunStart.size() + 1);
+      CK(cudaMemcpyAsync(c->dColorRunStart.p, c->colorRunStart.data(), c->colorRunStart.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->partRemaining.ensure(c->nPart + 1);
+    CK(cudaMemcpyAsync(c->partRemaining.p, c->hPartCount.data(), c->nPart * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(c->nPart * PGS_CLUSTER);
+    cfg.blockDim = dim3(128);
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PGS_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const int *pr = c->partRange.p, *pss = c->partSceneStart.p, *dcs = c->dColorStart.p, *dcr = hubs ? c->dColorRunStart.p : nullptr;
+    int* prem = c->partRemaining.p;
+    double* dvp = c->dv.p;
+    unsigned long long* isp = c->iterState.p;
+    if (hubs) CK(cudaLaunchKernelEx(&cfg, k_pgs_cluster<true>, pr, pss, prem, dcs, dcr, HR, S, dvp, PP, iterations, isp));
+    else CK(cudaLaunchKernelEx(&cfg, k_pgs_cluster<false>, pr, pss, prem, dcs, dcr, HR, S, dvp, PP, iterations, isp));
+    c->kernelLaunches++;
+    if (!sweep) c->solveLaunches++;
+  } else if (persistent) {
     int nColors = c->nColors;
     const int* dcs = c->dColorStart.p;
     const int* dcr = nullptr;

@@ -816,13 +816,27 @@ k_color_coop(int ng, int ns, int maxPages, const int* __restrict__ sb1, const in
 // share no free body) by descending contact count so that the lanes of a warp run the same number of contacts; ties by
 // group index (the radix sort is stable).  layer = breadth-first distance from the body pairs that hold new contacts
 // (getOrganizedContacts, CollisionProcessor.java:346-441) for the single sweep, absent (0) for the full solve.
+// partShift > 0: batched scenes are solved in PARTITIONS (blocks of consecutive scenes, one thread-block cluster each):
+// the partition leads the key, so that every partition's phases are contiguous
 __global__ void k_color_sortkey(int ng, const int* __restrict__ color, const int* __restrict__ gcount, const int* __restrict__ layer,
+                                const int* __restrict__ gb1, const int* __restrict__ bodyScene, int partShift, int nPart, int nScenes,
                                 unsigned long long* __restrict__ key, int* __restrict__ val) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ng) return;
   unsigned long long L = layer ? (unsigned long long)(unsigned)layer[g] : 0ULL;
-  key[g] = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
+  unsigned long long k = (L << 20) | ((unsigned long long)(unsigned)color[g] << 8) | (unsigned)(255 - min(gcount[g], 255));
+  if (partShift > 0) k |= (unsigned long long)((long long)bodyScene[gb1[g]] * nPart / nScenes) << partShift;
+  key[g] = k;
   val[g] = g;
+}
+// per partition: its range of phases (partitions without groups keep begin = end = 0)
+__global__ void k_part_phases(int nPhases, const int* __restrict__ phaseStart, const unsigned long long* __restrict__ key, int partShift,
+                              int* __restrict__ partRange /* [2 * nPart] */) {
+  int ph = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ph >= nPhases) return;
+  int s = (int)(key[phaseStart[ph]] >> partShift);
+  if (ph == 0 || (int)(key[phaseStart[ph - 1]] >> partShift) != s) partRange[2 * s] = ph;
+  if (ph == nPhases - 1 || (int)(key[phaseStart[ph + 1]] >> partShift) != s) partRange[2 * s + 1] = ph + 1;
 }
 // phases of the sorted group list: head = first group of a (layer, colour) class
 __global__ void k_phase_heads(int ng, const unsigned long long* __restrict__ key, int* __restrict__ head) {
@@ -1064,16 +1078,15 @@ __device__ __forceinline__ double divExact(double a, double b, double y) {
 // 4096 than the grid-wide sweeps, which keep every SM busy with whatever scene has work.)
 template <int MODE, bool HUB>
 __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __restrict__ dv, const PgsParams& P, int lastIter) {
-  int scene = 0;
-  if (MODE == 1 && P.check) {
-    scene = S.sgScene[p];
-    if (S.sceneState[scene]) return;  // this scene has left the iteration
-  }
+  // (the header loads are issued before the scene's done flag is looked at: the two dependent loads of that test would
+  // otherwise delay everything behind them by a memory round trip per phase)
+  int scene = (MODE == 1 && P.check) ? S.sgScene[p] : 0;
   double localMax = 0;
   int a = S.sgB1[p], b = S.sgB2[p];
   int start = S.sgStart[p], cnt = S.sgCount[p];
   const double* PK0 = S.scP + 24 * (size_t)start;
   if (cnt > 0) { prefetchL2(PK0); prefetchL2(PK0 + 16); }
+  if (MODE == 1 && P.check && S.sceneState[scene]) return;  // this scene has left the iteration
   double M[20];
   const double* Mp = S.sgMass + 20 * (size_t)p;
 #pragma unroll
@@ -1204,7 +1217,8 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
 }
 // end of an iteration, one thread per scene: count it, and retire the scenes nobody marked as moving
 // iterState: [1] every scene is done, [2] largest iteration count, [6] scenes still iterating
-__device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __restrict__ sceneState, unsigned long long* __restrict__ iterState) {
+__device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __restrict__ sceneState, unsigned long long* __restrict__ iterState,
+                                             int* partRemaining = nullptr) {
   if (sceneState[s]) return;
   int it = ++sceneState[P.nScenes + s];
   atomicMax(iterState + 2, (unsigned long long)it);
@@ -1215,6 +1229,7 @@ __device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __r
   if (P.check && !moving) {
     sceneState[s] = 1;
     if (atomicAdd(iterState + 6, (unsigned long long)-1LL) == 1ULL) iterState[1] = 1;
+    if (partRemaining) atomicSub(partRemaining, 1);
   }
 }
 
@@ -1491,6 +1506,56 @@ k_pgs_persistent(int nColors, const int* __restrict__ colorStart, const int* __r
     for (int s = tid; s < P.nScenes; s += stride) sceneIterEnd(s, P, S.sceneState, iterState);
     grid.sync();
     if (((volatile unsigned long long*)iterState)[1]) break;
+  }
+}
+// Batched scenes, one THREAD-BLOCK CLUSTER per partition of scenes.  Scenes never interact, so a phase barrier only has to
+// cover the scenes that share the barrier: instead of one grid-wide barrier per phase (k_pgs_persistent: every CTA waits
+// for the slowest group of ALL scenes, and for the barrier's own latency across 296 CTAs) the scenes are cut into as many
+// partitions as clusters fit the GPU, each cluster walks the phases of ITS scenes with the hardware cluster barrier
+// (barrier.cluster arrive.release / wait.acquire) and the partitions drift apart freely.  Same Gauss-Seidel sequence per
+// scene, so the results are bit-identical to the other sweep forms.
+#define PGS_CLUSTER 8
+template <bool HUB>
+__global__ void __launch_bounds__(128)
+k_pgs_cluster(const int* __restrict__ partRange, const int* __restrict__ partSceneStart, int* __restrict__ partRemaining,
+              const int* __restrict__ colorStart, const int* __restrict__ colorRunStart, HubRuns H, SolveArrays S,
+              double* __restrict__ dv, PgsParams P, int iterations, unsigned long long* __restrict__ iterState) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int part = blockIdx.x / PGS_CLUSTER;
+  const int tid = (int)cl.thread_rank(), stride = (int)cl.num_threads();
+  const int warp = tid >> 5, nwarps = stride >> 5;
+  const int ph0 = partRange[2 * part], ph1 = partRange[2 * part + 1];
+  if (ph1 <= ph0) return;  // (uniform over the cluster)
+  for (int c = ph0; c < ph1; c++) {
+    int g1 = colorStart[c + 1];
+    for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<0, HUB>(p, S, dv, P, 0);
+    cl.sync();
+    if (HUB) {
+      int r1 = colorRunStart[c + 1];
+      if (r1 > colorRunStart[c]) {
+        for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, nullptr);
+        cl.sync();
+      }
+    }
+  }
+  const int s0 = partSceneStart[part], s1 = partSceneStart[part + 1];
+  for (int it = 0; it < iterations; it++) {
+    int last = it == iterations - 1;
+    for (int c = ph0; c < ph1; c++) {
+      int g1 = colorStart[c + 1];
+      for (int p = colorStart[c] + tid; p < g1; p += stride) pgsGroup<1, HUB>(p, S, dv, P, last);
+      cl.sync();
+      if (HUB) {
+        int r1 = colorRunStart[c + 1];
+        if (r1 > colorRunStart[c]) {
+          for (int r = colorRunStart[c] + warp; r < r1; r += nwarps) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, P.check ? S.sceneState : nullptr);
+          cl.sync();
+        }
+      }
+    }
+    for (int s = s0 + tid; s < s1; s += stride) sceneIterEnd(s, P, S.sceneState, iterState, partRemaining + part);
+    cl.sync();
+    if (P.check && __ldcg(partRemaining + part) <= 0) break;
   }
 }
 __global__ void k_iter_end(SolveArrays S, PgsParams P, unsigned long long* __restrict__ iterState) {

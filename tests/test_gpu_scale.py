@@ -99,12 +99,14 @@ def test_batched_copies_agree():
     s.close()
 
 
-def test_scene_in_a_batch_equals_the_scene_alone():
+@pytest.mark.parametrize("copies", [8, 80])
+def test_scene_in_a_batch_equals_the_scene_alone(copies):
     """Scene k of a batched context == the same scene run alone in its own context, bit for bit: body states, contact
     multipliers, merge / unmerge events and PGS iteration counts.  The copies get different initial kicks, so they
-    collapse differently and leave the PGS at different iteration counts (per-scene tolerance exit, PGS.java:190-192)."""
+    collapse differently and leave the PGS at different iteration counts (per-scene tolerance exit, PGS.java:190-192).
+    8 copies run the grid-wide sweeps, 80 copies the partitioned ones (one thread-block cluster per block of scenes)."""
     one = golden_scene("tower25platform")
-    copies, steps = 8, 170
+    steps = 170
     nb = one.a["body_type"].shape[0]
     p = apply_overrides(default_params(), one.overrides)
     kicked = one.names.index("B3L0")
@@ -115,15 +117,16 @@ def test_scene_in_a_batch_equals_the_scene_alone():
 
     batch = one.replicate(copies)
     for k in range(copies):
-        kick(batch, k, k)
+        kick(batch, k, k % 8)
     s = RigidBodySystem(0).load(batch, p)
     s.advanceTime(0.05, steps)
     bb, cb, eb = s.bodies(), s.contacts(), s.events()
+    s_launches = s.stats()["solve_launches"]
     s.close()
     assert len(eb) > 0
-    for k in (0, 3, 7):
+    for k in (0, 3, copies - 1):
         alone = one.replicate(1)
-        kick(alone, 0, k)
+        kick(alone, 0, k % 8)
         a = RigidBodySystem(0).load(alone, p)
         a.advanceTime(0.05, steps)
         ba, ca, ea = a.bodies(), a.contacts(), a.events()
@@ -141,3 +144,5 @@ def test_scene_in_a_batch_equals_the_scene_alone():
     # the copies really differ
     x = bb["x"].reshape(copies, nb, 3)
     assert np.abs(x[7] - x[0]).max() > 1e-3
+    if copies >= 80:
+        assert s_launches < 0.5 * steps * 60, s_launches  # one launch per solve, not one per phase
