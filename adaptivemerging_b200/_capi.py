@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libam3d.so")
+LIB_PATH = os.environ.get("AM3D_LIBRARY") or os.path.join(_HERE, "libam3d.so")  # (AM3D_LIBRARY: another build of the same library, for A/B runs)
 
 OK, EINVAL, ECUDA, ENOGPU, EUNSUPPORTED, ECAPACITY, ESTATE = 0, -1, -2, -3, -4, -5, -6
 

@@ -219,7 +219,7 @@ struct am3d_ctx {
   DevBuf<unsigned long long> tailKey, tailKeySorted;
   DevBuf<int> tailVal, tailIdx;
   DevBuf<unsigned long long> wsKa, wsKb, wsK0s, wsK1s;  // (key0,key1)-sorted index of last step's contacts
-  DevBuf<int> wsIa, wsIb, wsIdx;
+  DevBuf<int> wsIa, wsIb, wsIdx, wsPairSlow, wsMatch;
   DevBuf<double> B2CR, B2Ct;  // RigidBody.transformB2C of the leaves
   DevBuf<int> collCount, collStart, members, memVal, changedList, collMode, collFlagAcc, freeList;
   DevBuf<unsigned int> memKey, memKeySorted;

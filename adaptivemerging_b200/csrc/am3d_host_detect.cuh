@@ -127,6 +127,8 @@ static void warmStart(am3d_ctx* c, bool postStab = false) {
       return cub::DeviceRadixSort::SortPairs(t, b, c->tailKey.p, c->tailKeySorted.p, c->tailVal.p, c->tailIdx.p, nt, 0, 64, c->stream);
     });
   }
+  c->wsPairSlow.ensure(nbp + 1); c->wsMatch.ensure(c->cur.n + 1);
+  CK(cudaMemsetAsync(c->wsPairSlow.p, 0, nbp * sizeof(int), c->stream));
   int ns = c->prev.nSorted;
   // a pair of sphere trees can hold 10^4+ contacts: index last step's contacts when it had such pairs
   int useIdx = c->NN > 0 && ns > 0 && readInt(c, c->counters.p + 8 + (c->bpSlot ^ 1)) > 64;
@@ -147,8 +149,9 @@ static void warmStart(am3d_ctx* c, bool postStab = false) {
             c->cur.lam.p, c->cur.lamWarm.p, c->cur.prevViol.p, c->cur.isNew.p,
             c->prev.n, c->prev.nSorted, c->cur.n, c->tailKeySorted.p, c->tailIdx.p, c->prev.key0.p, c->prev.key1.p, c->prev.b1.p, c->prev.leaf.p, c->prev.pB1.p, postStab ? c->prev.prevViol.p : c->prev.viol.p, c->prev.lam.p,
             useIdx, c->wsK0s.p, c->wsK1s.p, c->wsIdx.p,
-            c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p};
+            c->btype.p, c->shType.p, c->x.p, c->R.p, c->ndRank.p, c->cur.bpc.p, c->wsPairSlow.p, c->wsMatch.p};
   LAUNCH(c, k_warm_start_plain, nblk(c->cur.n), BLK, c->cur.n, W);
+  LAUNCH(c, k_warm_apply, nblk(c->cur.n), BLK, c->cur.n, W);
   LAUNCH(c, k_warm_start, nblk(nbp, 128), 128, nbp, c->bp.start.p, c->bp.count.p, c->bp.b1.p, c->bp.b2.p, W);
 }
 

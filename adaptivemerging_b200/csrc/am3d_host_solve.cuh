@@ -265,6 +265,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   // launch per colour (no barrier cost, full occupancy per launch)
   long long avgGroups = ng / std::max(1, c->nColors);
   bool persistent = nGiants == 0 && c->coopBlocks > 0 && c->usePersistent != 0 && (c->usePersistent == 2 || avgGroups < 4 * (long long)c->coopBlocks * 128);
+  if (!sweep && !post) { c->T.pgs_kernel = (c->nPart > 0 && nGiants == 0) ? 2 : persistent ? 1 : 0; c->T.pgs_giant_groups = nGiants; }
   if (c->nPart > 0 && nGiants == 0) {
     bool hubs = c->nHubRuns > 0;
     if (hubs) {

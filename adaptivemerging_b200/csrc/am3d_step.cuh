@@ -315,6 +315,10 @@ struct WarmCtx {
   const int *btype, *shType;
   const double *x, *R;
   const int* ndRank;
+  // box-box fast path: contact -> body pair, pairs that need the sequential repair, direct matches
+  const int* bpc;
+  int* pairSlow;
+  int* matchIdx;
 };
 
 // find the previous contact equal to (key0, key1); duplicate keys (box x tree leaf hits, Appendix B):
@@ -399,19 +403,49 @@ __device__ __forceinline__ void warmRange(const WarmCtx& W, unsigned long long k
   rhi = lo;
 }
 
-// pairs without a box-box part (CollisionProcessor.java:479-495): plain key lookup, nothing is taken away from the
-// donor, so the contacts of a pair are independent -> one thread per contact
+// One thread per contact.
+// Pairs without a box-box part (CollisionProcessor.java:479-495): plain key lookup, nothing is taken away from the donor,
+// so the contacts of a pair are independent.
+// Box-box pairs (:505-640): the common case is that every contact of the pair finds last step's contact of the same
+// (key, info) within 0.05 - then no contact looks at another one's donor and the order inside the pair does not matter:
+// the direct match is recorded here and applied by k_warm_apply.  A contact that misses marks its PAIR for the
+// sequential repair path (k_warm_start), which then redoes that pair from scratch exactly as the reference does.
 __global__ void k_warm_start_plain(int nc, WarmCtx W) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   int t1 = W.btype[W.b1[i]], t2 = W.btype[W.b2[i]];
   bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
-  if (boxy) return;
   unsigned long long k0 = W.key0[i], k1 = W.key1[i];
   int rlo, rhi;
+  if (!boxy) {
+    warmRange(W, k0, (int)((long long)i * W.npSorted / max(nc, 1)), rlo, rhi);
+    int j = warmLookup(W, rlo, rhi, k0, k1);
+    if (j >= 0) warmTake(W, i, j, false); else W.isNew[i] = 1;
+    return;
+  }
+  int pair = W.bpc[i];
+  if (pair < 0) return;
+  W.matchIdx[i] = -1;
+  bool nb1 = t1 == AM3D_BODY_COMPOSITE && W.shType[W.s1[i]] != AM3D_SHAPE_BOX;
+  bool nb2 = t2 == AM3D_BODY_COMPOSITE && W.shType[W.s2[i]] != AM3D_SHAPE_BOX;
+  if (nb1 || nb2) { W.pairSlow[pair] = 1; return; }
   warmRange(W, k0, (int)((long long)i * W.npSorted / max(nc, 1)), rlo, rhi);
   int j = warmLookup(W, rlo, rhi, k0, k1);
-  if (j >= 0) warmTake(W, i, j, false); else W.isNew[i] = 1;
+  if (j < 0) { W.pairSlow[pair] = 1; return; }
+  d3 pNew = worldPoint(W.x, W.R, W.b1[i], ld3(W.pB1 + 3 * i));
+  d3 pOld = worldPoint(W.x, W.R, W.pb1[j], ld3(W.ppB1 + 3 * j));
+  if (vdist(pNew, pOld) < 0.05) W.matchIdx[i] = j;
+  else W.pairSlow[pair] = 1;
+}
+__global__ void k_warm_apply(int nc, WarmCtx W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  int t1 = W.btype[W.b1[i]], t2 = W.btype[W.b2[i]];
+  bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
+  if (!boxy) return;
+  int pair = W.bpc[i];
+  if (pair < 0 || W.pairSlow[pair]) return;
+  warmTake(W, i, W.matchIdx[i], true);
 }
 
 __global__ void k_gather_u64(int n, const int* __restrict__ idx, const unsigned long long* __restrict__ src,
@@ -428,6 +462,7 @@ __global__ void k_warm_start(int nbp, const int* __restrict__ bstart, const int*
   int t1 = W.btype[bb1[b]], t2 = W.btype[bb2[b]];
   bool boxy = (t1 == AM3D_BODY_BOX || t1 == AM3D_BODY_COMPOSITE) && (t2 == AM3D_BODY_BOX || t2 == AM3D_BODY_COMPOSITE);
   if (!boxy) return;  // k_warm_start_plain
+  if (!W.pairSlow[b]) return;  // every contact matched directly: k_warm_apply
   unsigned long long lastK0 = ~0ULL;
   int rlo = 0, rhi = 0;
   for (int i = s; i < e; i++) {
@@ -1456,8 +1491,11 @@ __global__ void k_hub_reduce(int rBegin, int rEnd, HubRuns H, SolveArrays S, dou
   if (r < rEnd) hubReduceRun(r, H, S.hubDelta, dv, S.sgScene, (mode == 1 && check) ? S.sceneState : nullptr);
 }
 
+#ifndef PGS_MIN_BLOCKS
+#define PGS_MIN_BLOCKS 1  // (a register cap for 3 CTAs per SM was measured again in round 2)
+#endif
 template <int MODE, bool HUB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, PGS_MIN_BLOCKS)
 k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
             unsigned long long* __restrict__ iterState) {
   if (MODE == 1 && iterState[1]) return;  // every scene has taken its tolerance exit (PGS.java:190-192)

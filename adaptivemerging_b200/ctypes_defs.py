@@ -87,6 +87,7 @@ class am3d_timings(C.Structure):
         ("unmerging_build", C.c_double), ("compute_time", C.c_double),
         ("pgs_iterations", C.c_int32), ("pgs_colors", C.c_int32), ("n_pairs", C.c_int32), ("n_collections", C.c_int32),
         ("pgs_kernel_time", C.c_double), ("narrowphase_kernel_time", C.c_double),
+        ("pgs_kernel", C.c_int32), ("pgs_giant_groups", C.c_int32),
     ]
 
 

@@ -225,7 +225,7 @@ def run_leg(local, blob, params, steps, warmup, settle, with_e2e, barrier):
            "row_updates": s1["row_updates"] - s0["row_updates"], "solve_s": s1["solve_seconds"] - s0["solve_seconds"],
            "series": series, "launches": s1["kernel_launches"] - s0["kernel_launches"], "solve_launches": s1["solve_launches"] - s0["solve_launches"],
            "tm": {"n_collections": tm.n_collections, "n_contacts": tm.n_contacts, "n_pairs": tm.n_pairs, "pgs_colors": tm.pgs_colors,
-                  "n_bodies_top_level": tm.n_bodies,
+                  "n_bodies_top_level": tm.n_bodies, "pgs_kernel": tm.pgs_kernel, "pgs_giant_groups": tm.pgs_giant_groups,
                   "phase_ms": {"detection": tm.detection * 1e3, "warmstart": tm.warmstart * 1e3, "update_collections": tm.update_collections * 1e3,
                                "contact_ordering": tm.contact_ordering * 1e3, "single_it_pgs": tm.single_it_pgs * 1e3,
                                "unmerging": tm.unmerging * 1e3, "lcp_solve": tm.lcp_solve * 1e3, "pgs_sweeps": tm.pgs_kernel_time * 1e3,
@@ -274,8 +274,9 @@ def roofline_of(leg, workload, steps):
     row_updates, solve_s = leg["row_updates"], leg["solve_s"]
     achieved = (row_updates / 3.0) * PGS_BYTES_PER_CONTACT_ITER / max(solve_s, 1e-12) / 1e9
     solve_launches = max(float(leg["solve_launches"]), 1.0)
-    persistent = solve_launches <= 2 * steps  # one cooperative launch per solve vs one launch per colour per iteration
-    kernel = "k_pgs_persistent" if persistent else "k_pgs_color<1>"
+    kernel = {0: "k_pgs_color<1>", 1: "k_pgs_persistent", 2: "k_pgs_cluster"}[leg["tm"]["pgs_kernel"]]
+    if leg["tm"]["pgs_giant_groups"]:
+        kernel = "k_pgs_giant<1> + " + kernel
     traffic_ratio, traffic_src = measured_traffic(kernel, workload)
     contact_iters_per_launch = (row_updates / 3.0) / solve_launches
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -226,6 +226,9 @@ typedef struct am3d_timings {
   int32_t n_collections;
   double pgs_kernel_time; /* device time of the full-solve sweeps only */
   double narrowphase_kernel_time; /* device time of the narrowphase kernels (count + emit passes) */
+  int32_t pgs_kernel;     /* sweep form of the last full solve: 0 k_pgs_color (one launch per phase), 1 k_pgs_persistent
+                             (one cooperative launch), 2 k_pgs_cluster (one launch, a thread-block cluster per block of scenes) */
+  int32_t pgs_giant_groups; /* groups of >= 65 contacts solved by k_pgs_giant in the last full solve */
 } am3d_timings;
 
 /* One contact as the tests and the Java mirror see it (Contact.java fields). */
