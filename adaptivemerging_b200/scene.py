@@ -22,6 +22,8 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from .volint import mesh_mass_properties  # VolInt / Polyhedron / PolygonSoup arithmetic (XMLParser.createMesh :457-464)
+
 BODY_BOX, BODY_PLANE, BODY_SPHERE, BODY_MESH, BODY_COMPOSITE = 0, 1, 2, 3, 4
 SHAPE_BOX, SHAPE_TREE, SHAPE_PLANE = 0, 1, 2
 F_PINNED, F_MAGNETIC, F_MAGNET_ACTIVE, F_SLEEPING = 1, 2, 4, 8
@@ -279,39 +281,6 @@ def _flatten_tree(cB, rr, children, root):
 def single_sphere_tree(r):
     return Tree(c=np.zeros((1, 3)), r=np.array([float(r)]), first_child=np.array([-1], dtype=np.int32),
                 child_count=np.array([0], dtype=np.int32), rank=np.array([0], dtype=np.int32))
-
-
-def mesh_mass_properties(obj_path, scale, density):
-    """Mass, inertia about the COM and COM of a closed triangle mesh (first three vertices of every
-    face, as PolygonSoup.getPolyhedron does).  The reference evaluates Mirtich's face-integral
-    formulation (tools/moments/VolInt.java:318-384, load time only, OUT OF SCOPE §2 row 15); this
-    uses the mathematically identical signed-tetrahedron sums, vectorised."""
-    verts = []
-    faces = []
-    with open(obj_path) as f:
-        for line in f:
-            if line.startswith("v "):
-                t = line[2:].split()
-                verts.append([float(t[0]), float(t[1]), float(t[2])])
-            elif line.startswith("f "):
-                t = line[2:].split()
-                faces.append([int(t[i].split("/")[0]) - 1 for i in range(3)])
-    V = np.array(verts) * scale
-    F = np.array(faces)
-    a, b, c = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
-    det = np.einsum("ij,ij->i", a, np.cross(b, c))
-    vol = det.sum() / 6.0
-    com = ((a + b + c) * det[:, None]).sum(0) / (24.0 * vol)
-    # second moments  ∫ x_i x_j dV over a tetra (0,a,b,c) = det/120 * (sum over pairs ...)
-    S = a + b + c
-    cov = (np.einsum("n,ni,nj->ij", det, a, a) + np.einsum("n,ni,nj->ij", det, b, b)
-           + np.einsum("n,ni,nj->ij", det, c, c) + np.einsum("n,ni,nj->ij", det, S, S)) / 120.0
-    tr = np.trace(cov)
-    J = density * (tr * np.eye(3) - cov)
-    mass = density * vol
-    r = com
-    J = J - mass * ((r @ r) * np.eye(3) - np.outer(r, r))
-    return mass, J, com, V
 
 
 class SceneBuilder:
