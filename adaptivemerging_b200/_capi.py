@@ -20,7 +20,7 @@ EXPORTS = [
     "am3d_num_events", "am3d_download_events", "am3d_record_orders", "am3d_download_order", "am3d_num_internal_bpcs",
     "am3d_download_internal_bpcs", "am3d_download_collection", "am3d_set_option", "am3d_add_velocities",
     "am3d_download_bodies_async", "am3d_wait_download", "am3d_download_list_order", "am3d_set_body_sleeping",
-    "am3d_activate_body", "am3d_remove_body", "am3d_set_mouse_spring", "am3d_apply_impulse",
+    "am3d_activate_body", "am3d_remove_body", "am3d_set_mouse_spring", "am3d_apply_impulse", "am3d_set_body_magnet",
 ]
 
 _LIB = None
@@ -53,6 +53,7 @@ def load():
         L.am3d_download_collection.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.am3d_num_contacts.argtypes = [C.c_void_p, C.c_int]
         L.am3d_set_body_sleeping.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.am3d_set_body_magnet.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.am3d_activate_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.am3d_remove_body.argtypes = [C.c_void_p, C.c_int]
         L.am3d_set_mouse_spring.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int]

@@ -310,7 +310,13 @@ static void waitPending(am3d_ctx* c) {
 static void checkParams(const am3d_params* p) {
   // shuffle (Collections.shuffle with an unseeded Random, CollisionProcessor.java:674): asks for an unspecified order of the
   // Gauss-Seidel sweep; the colour order already is one (and stays deterministic), so the flag is accepted as it is
-  if (p->collection_cd != 0) throw AmError(AM3D_EUNSUPPORTED, "only the brute-force collection collision mode is supported");
+  // collectionCD (CollisionProcessor.java:768-790): 0 = brute force over the members, 1 = the collection's sphere BVH
+  // (:859-912, RigidCollection.java:184-453), 2 = world-AABB test per member pair (:921-960).  Modes 1 and 2 only PRUNE the
+  // narrowPhase(member, other) calls of mode 0 with bounding volumes that enclose the members (BVSphere(body) encloses the
+  // body's bounding box, getEnclosingSphere :414-453 encloses both children, sweepCollide compares the world boxes), so
+  // all three modes yield the same contacts; they differ in the order contacts enter the list, which this library replaces by
+  // its canonical order anyway.  Detection here always prunes leaf-body pairs by world AABB, whatever the mode.
+  if (p->collection_cd < 0 || p->collection_cd > 2) throw AmError(AM3D_EINVAL, "collection_cd must be 0 (brute force), 1 (BVH) or 2 (sweep and prune)");
   if (p->merge_cycle_condition) throw AmError(AM3D_EUNSUPPORTED, "cycle merge condition is not supported");
   if (p->iterations < 1 || p->iterations_in_collection < 1) throw AmError(AM3D_EINVAL, "iterations must be >= 1");
   if (p->step_accum_merging > 4 || p->step_accum_unmerging > 4 || p->step_accum_merging < 0) throw AmError(AM3D_EUNSUPPORTED, "accumulation windows above 4 steps are not supported");
@@ -614,6 +620,21 @@ int am3d_set_body_sleeping(am3d_ctx* c, int body, int sleeping) {
   CK(cudaMemcpy(&fl, c->flags.p + body, sizeof(int), cudaMemcpyDeviceToHost));
   fl = sleeping ? (fl | AM3D_F_SLEEPING) : (fl & ~AM3D_F_SLEEPING);
   CK(cudaMemcpy(c->flags.p + body, &fl, sizeof(int), cudaMemcpyHostToDevice));
+  API_END(c)
+}
+
+// LCPApp3D.java:936-947 (key 7): `if (b.magnetic) b.activateMagnet = !b.activateMagnet` for every body and every member of a
+// collection; PGS.java:119,150,167 then leaves the multipliers of a contact with an active magnet unclamped.  The flag is
+// read when the solve order is set up (k_group_setup), i.e. from the next step on.  A body that is not magnetic keeps its flags.
+int am3d_set_body_magnet(am3d_ctx* c, int body, int active) {
+  API_BEGIN(c)
+  if (!c->haveScene || body < 0 || body >= c->NB) throw AmError(AM3D_EINVAL, "bad body index");
+  int fl;
+  CK(cudaMemcpy(&fl, c->flags.p + body, sizeof(int), cudaMemcpyDeviceToHost));
+  if (fl & AM3D_F_MAGNETIC) {
+    fl = active ? (fl | AM3D_F_MAGNET_ACTIVE) : (fl & ~AM3D_F_MAGNET_ACTIVE);
+    CK(cudaMemcpy(c->flags.p + body, &fl, sizeof(int), cudaMemcpyHostToDevice));
+  }
   API_END(c)
 }
 

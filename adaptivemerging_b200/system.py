@@ -174,6 +174,10 @@ class RigidBodySystem:
     def set_body_sleeping(self, body, sleeping):
         self._ck(self._L.am3d_set_body_sleeping(self._h, int(body), int(bool(sleeping))))
 
+    def set_body_magnet(self, body, active):
+        """RigidBody.activateMagnet as LCPApp3D's key 7 toggles it (:936-947)"""
+        self._ck(self._L.am3d_set_body_magnet(self._h, int(body), int(bool(active))))
+
     def activate_body(self, body, x, R=None, v=None, omega=None):
         """RigidBodySystem.add of a dormant clone (Factory.generateBody)"""
         a = [np.ascontiguousarray(q, np.float64) if q is not None else None for q in (x, R, v, omega)]

@@ -150,10 +150,11 @@ typedef struct am3d_scene {
 typedef struct am3d_params {
   /* CollisionProcessor.java:1058-1083, Contact.java:518 */
   int32_t warm_start;
-  int32_t shuffle;                 /* unsupported (must be 0) */
-  int32_t enable_post_stabilization; /* unsupported (must be 0) */
+  int32_t shuffle;                 /* CollisionProcessor.java:674: asks for an unspecified sweep order; accepted, the colour order is one */
+  int32_t enable_post_stabilization; /* RigidBodySystem.java:354-377, PGS.java:86-89 */
   int32_t enable_compliance;
-  int32_t collection_cd;           /* 0 = brute force over members (only mode built) */
+  int32_t collection_cd;           /* 0 brute force, 1 BVH, 2 sweep and prune (:768-790): pruning structures over the same member
+                                      pair tests - identical contacts; detection here prunes by world AABB in every mode */
   int32_t restitution_override;
   int32_t friction_override;
   int32_t iterations;
@@ -168,7 +169,7 @@ typedef struct am3d_params {
   double sliding_threshold;
   /* RigidBodySystem.java:544-554 */
   int32_t use_gravity;
-  int32_t use_coriolis;            /* unsupported (must be 0) */
+  int32_t use_coriolis;            /* RigidBodySystem.java:212-229, 295-304 */
   int32_t springs_enabled;         /* reference applies springs only if mouseSpring != null (:244-247) */
   int32_t _pad1;
   double gravity_amount;
@@ -189,7 +190,7 @@ typedef struct am3d_params {
   int32_t unmerge_relative_motion;
   int32_t update_contacts_in_collections;
   int32_t organize_contacts;
-  int32_t metric_position_level;   /* unsupported (must be 0) */
+  int32_t metric_position_level;   /* MotionMetricProcessor.java:75-116 */
   int32_t step_accum_merging;
   int32_t step_accum_unmerging;
   int32_t steps_between_merge;
@@ -290,6 +291,10 @@ int am3d_set_body_velocity(am3d_ctx* ctx, int body, const double v[3], const dou
 int am3d_add_body_velocity(am3d_ctx* ctx, int body, const double dv[3], const double domega[3]);
 /* Animation.applyNonPersistant (Animation.java:82-160) writes `body.sleeping = false` next to the velocity it sets */
 int am3d_set_body_sleeping(am3d_ctx* ctx, int body, int sleeping);
+/* LCPApp3D.java:936-947 (key 7) toggles RigidBody.activateMagnet of the magnetic bodies (RigidBody.java:149-153,
+ * XML tag <magnetic>, XMLParser.java:587); contacts of a body with an active magnet are solved without the
+ * non-negativity / friction-cone clamps (PGS.java:119,150,167).  No effect on a body that is not magnetic. */
+int am3d_set_body_magnet(am3d_ctx* ctx, int body, int active);
 /* RigidBodySystem.add(body) (:78) as Factory.generateBody uses it (Factory.java:99-116): a DORMANT body of the scene blob
  * (a clone of a factory part) enters RigidBodySystem.bodies at the end of the list with the given state.
  * R = NULL: identity, v / omega = NULL: zero. */

@@ -58,6 +58,7 @@ final class AM3DNative implements AutoCloseable {
             FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_DOUBLE, JAVA_DOUBLE, JAVA_INT));
     private static final MethodHandle APPLY_IMPULSE = h("am3d_apply_impulse", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_DOUBLE));
     private static final MethodHandle SET_BODY_SLEEPING = h("am3d_set_body_sleeping", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
+    private static final MethodHandle SET_BODY_MAGNET = h("am3d_set_body_magnet", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT));
     private static final MethodHandle LIST_ORDER = h("am3d_download_list_order", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle STEP_ASYNC = h("am3d_step_async", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE, JAVA_INT));
     private static final MethodHandle SYNC = h("am3d_sync", FunctionDescriptor.of(JAVA_INT, ADDRESS));
@@ -127,6 +128,8 @@ final class AM3DNative implements AutoCloseable {
     void setMouseSpring(int body, MemorySegment grabPointB, MemorySegment pointW, double k, double c, boolean atCOM) { try { check((int) SET_MOUSE_SPRING.invokeExact(ctx, body, grabPointB, pointW, k, c, atCOM ? 1 : 0)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     /** MouseImpulse.release(): applied inside the next step */
     void applyImpulse(int body, MemorySegment pickedPointB, MemorySegment endPointW, double scale) { try { check((int) APPLY_IMPULSE.invokeExact(ctx, body, pickedPointB, endPointW, scale)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
+    /** RigidBody.activateMagnet as LCPApp3D's key 7 toggles it (LCPApp3D.java:936-947) */
+    void setBodyMagnet(int body, boolean active) { try { check((int) SET_BODY_MAGNET.invokeExact(ctx, body, active ? 1 : 0)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     void setBodySleeping(int body, boolean sleeping) { try { check((int) SET_BODY_SLEEPING.invokeExact(ctx, body, sleeping ? 1 : 0)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }
     /** monotone position keys of every leaf's top-level entity: sort by them to rebuild system.bodies in the reference's order */
     void listOrder(MemorySegment int64PerBody) { try { check((int) LIST_ORDER.invokeExact(ctx, int64PerBody)); } catch (RuntimeException e) { throw e; } catch (Throwable t) { throw new RuntimeException(t); } }

@@ -2269,6 +2269,11 @@ void amo_add_body_velocity(void* h, int body, const double* dv, const double* do
   if (domega) t->omega = amo::add(t->omega, amo::V3(domega[0], domega[1], domega[2]));
 }
 void amo_set_body_sleeping(void* h, int body, int sleeping) { ((System*)h)->leaf[body]->sleeping = sleeping != 0; }
+// LCPApp3D.java:936-947: activateMagnet of a magnetic body
+void amo_set_body_magnet(void* h, int body, int active) {
+  amo::Body* b = ((System*)h)->leaf[body].get();
+  if (b->magnetic) b->activateMagnet = active != 0;
+}
 // RigidBodySystem.add (:78) of a dormant body (Factory.generateBody, Factory.java:99-116)
 void amo_activate_body(void* h, int body, const double* x, const double* R, const double* v, const double* omega) {
   System* s = (System*)h;

@@ -32,7 +32,7 @@ def lib():
         for name in ["amo_destroy", "amo_set_params", "amo_get_bodies", "amo_set_bodies", "amo_get_timings",
                      "amo_apply_external_forces", "amo_set_lambdas", "amo_get_deltav", "amo_set_next_orders",
                      "amo_get_events", "amo_set_body_velocity", "amo_add_body_velocity", "amo_residuals", "amo_get_list_order", "amo_set_next_order_post",
-                     "amo_set_body_sleeping", "amo_activate_body", "amo_remove_body", "amo_set_mouse_spring", "amo_apply_impulse"]:
+                     "amo_set_body_sleeping", "amo_set_body_magnet", "amo_activate_body", "amo_remove_body", "amo_set_mouse_spring", "amo_apply_impulse"]:
             getattr(L, name).restype = None
         for name in ["amo_row_updates", "amo_solve_seconds"]:
             getattr(L, name).restype = C.c_double
@@ -150,6 +150,9 @@ class Oracle:
 
     def set_body_sleeping(self, body, sleeping):
         self.L.amo_set_body_sleeping(self.h, int(body), int(bool(sleeping)))
+
+    def set_body_magnet(self, body, active):
+        self.L.amo_set_body_magnet(self.h, int(body), int(bool(active)))
 
     def activate_body(self, body, x, R=None, v=None, omega=None):
         a = [np.ascontiguousarray(q, np.float64) if q is not None else None for q in (x, R, v, omega)]

@@ -30,15 +30,38 @@ def test_call_order_and_bad_arguments():
     s.close()
 
 
-@pytest.mark.parametrize("field", ["merge_cycle_condition", "collection_cd"])
-def test_unsupported_reference_options_are_refused(field):
+def test_unsupported_reference_options_are_refused():
     s = RigidBodySystem(0)
     p = default_params()
-    setattr(p, field, 1)
+    p.merge_cycle_condition = 1
     with pytest.raises(_capi.Am3dError) as e:
         s.set_params(p)
     assert _code(e) == _capi.EUNSUPPORTED
+    p = default_params()
+    p.collection_cd = 3   # CollisionProcessor.java:788 "Unsupported collision detection method"
+    with pytest.raises(_capi.Am3dError) as e:
+        s.set_params(p)
+    assert _code(e) == _capi.EINVAL
     s.close()
+
+
+def test_collection_collision_modes_give_the_same_run():
+    """collectionCD 1 (BVH) and 2 (sweep and prune) prune the member-pair tests of mode 0 with enclosing volumes
+    (CollisionProcessor.java:768-790, 859-960): same contacts, same run."""
+    blob = small_pile(4, 5, 4)
+    runs = []
+    for mode in (0, 1, 2):
+        p = params()
+        p.collection_cd = mode
+        s = RigidBodySystem(0).load(blob, p)
+        s.advanceTime(0.05, 120)
+        runs.append((s.bodies(), s.events().tolist(), s.timings().n_contacts))
+        s.close()
+    assert len(runs[0][1]) > 0
+    for b, ev, nc in runs[1:]:
+        assert ev == runs[0][1] and nc == runs[0][2]
+        for k in ("x", "R", "v", "w"):
+            assert np.array_equal(b[k], runs[0][0][k]), k
 
 
 def test_reset_repeats_the_run_bit_for_bit():

@@ -91,3 +91,34 @@ def test_animation_style_velocity_writes():
         script[k] = (lambda s, r=(k - 89) / 20.0: (s.set_body_sleeping(b, 0), s.set_body_velocity(b, np.array([0.6 * r, 0.0, 0.0]), None)))
     gpu, cpu, ev_g, ev_o, worst = lockstep(blob, params(enable_merging=0), 140, script=script)
     assert ev_g == ev_o
+
+
+def test_magnet_holds_a_box_until_it_is_switched_off():
+    """RigidBody.magnetic / activateMagnet (RigidBody.java:149-153; toggled by LCPApp3D's key 7, :936-947): the contacts of a
+    body with an active magnet are solved without the clamps (PGS.java:119,150,167), so the multiplier can pull."""
+    from adaptivemerging_b200.scene import F_MAGNETIC, SceneBuilder
+    sb = SceneBuilder()
+    sb.add_plane((0, 0, 0), (0, 1, 0))
+    slab = sb.add_box((4, 1, 4), (0, 3.0, 0), pinned=True, name="magnet")
+    box = sb.add_box((1, 1, 1), (0.2, 2.01, -0.1), name="box")     # its top face sits 0.01 inside the slab's bottom face
+    sb.bodies[slab].magnetic = True
+    blob = sb.build()
+    assert blob.a["body_flags"][slab] & F_MAGNETIC
+    script = {0: lambda s: s.set_body_magnet(slab, 1), 60: lambda s: s.set_body_magnet(slab, 0),
+              3: lambda s: s.set_body_magnet(box, 1)}                # not magnetic: ignored
+    heights = []
+    p = params(enable_merging=0)
+
+    class Probe:   # record the height on the GPU side every step through the script hook
+        def __call__(self, s):
+            if hasattr(s, "_h"):
+                heights.append(float(s.bodies()["x"][box, 1]))
+    probe = Probe()
+    full = {k: (lambda s, f=script.get(k): (probe(s), f(s) if f else None)) for k in range(120)}
+    gpu, cpu, ev_g, ev_o, worst = lockstep(blob, p, 120, tol=1e-6, script=full)
+    assert ev_g == ev_o
+    assert min(heights[:60]) > 1.9, "the active magnet did not hold the box"
+    assert heights[-1] < 0.7, "the box did not fall after the magnet was switched off"
+    # and with merging on: same events on both sides
+    gpu, cpu, ev_g, ev_o, worst = lockstep(blob, params(), 120, tol=1e-6, script=script)
+    assert ev_g == ev_o

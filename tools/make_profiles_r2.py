@@ -40,6 +40,7 @@ def raw_rows(rep):
     if len(rows) < 3:
         return [], {}
     ix = {h: i for i, h in enumerate(rows[0])}
+    raw_rows.units = {h: rows[1][i] for h, i in ix.items()}
     return rows[2:], ix
 
 
@@ -154,6 +155,14 @@ def main():
         if not rows or bd is None:
             continue
         contacts = bd["contacts_last_step"]
+        try:  # the profiled run prints its own line: use ITS contact count
+            lg = [ln for ln in open(os.path.join(SRC, "ncu_" + name + ".log")) if ln.startswith("{")]
+            contacts = json.loads(lg[-1])["contacts_last_step"]
+        except Exception:
+            pass
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        ur = scale.get(raw_rows.units.get("dram__bytes_read.sum", ""), None)
+        uw = scale.get(raw_rows.units.get("dram__bytes_write.sum", ""), None)
         for kern, key in (("k_pgs_color<1", "k_pgs_color<1>"), ("k_pgs_persistent", "k_pgs_persistent")):
             sel = [r for r in rows if kern in r[ix["Kernel Name"]]]
             if not sel:
@@ -167,17 +176,22 @@ def main():
             else:
                 sel = [max(sel, key=lambda r: fnum(r[ix["gpu__time_duration.sum"]]))]
                 iters = 30
-            unit = 1e9 if "Gbyte" in "".join(rows[0]) else 1.0
             rd = sum(fnum(r[ix["dram__bytes_read.sum"]]) for r in sel)
             wr = sum(fnum(r[ix["dram__bytes_write.sum"]]) for r in sel)
             ms = sum(fnum(r[ix["gpu__time_duration.sum"]]) for r in sel)
             traffic.setdefault(key, {})[wl if name != "full_batch512" else "batch512"] = {
-                "dram_bytes_per_contact_iter": None, "raw_read": rd, "raw_write": wr, "raw_time": ms, "launches": len(sel),
+                "dram_bytes_per_contact_iter": None if ur is None or uw is None else (rd * ur + wr * uw) / (contacts * iters),
+                "raw_read": rd, "raw_write": wr, "raw_time": ms, "launches": len(sel),
                 "contacts": contacts, "iterations": iters,
                 "source": f"ncu --set full, profiles/r2_ncu_{name}.md: DRAM read + write of {len(sel)} launch(es) "
-                          f"(units as printed by ncu) / ({contacts} contacts x {iters} iteration(s))"}
+                          f"({raw_rows.units.get('dram__bytes_read.sum')}) / ({contacts} contacts x {iters} iteration(s))"}
     if traffic:
-        json.dump(traffic, open(os.path.join(DST, "r2_traffic_raw.json"), "w"), indent=1)
+        old = {}
+        if os.path.exists(os.path.join(DST, "r2_traffic.json")):  # keep the entries of earlier sessions' captures
+            old = json.load(open(os.path.join(DST, "r2_traffic.json")))
+        for k, v in traffic.items():
+            old.setdefault(k, {}).update(v)
+        json.dump(old, open(os.path.join(DST, "r2_traffic.json"), "w"), indent=1)
     f50 = os.path.join(SRC, "funnel50.jsonl")
     if os.path.exists(f50):
         shutil.copy(f50, os.path.join(DST, "r2_funnel50.jsonl"))
