@@ -243,6 +243,7 @@ struct am3d_ctx {
   int useClusters = 1, maxClusters = 0, nPart = 0, hPartScenes = 0;
   DevBuf<int> partRange, partSceneStart, partRemaining;
   std::vector<int> hPartSceneStart, hPartCount;
+  int fastRows = 1;       // am3d_set_option("pgs_fast_rows", 0/1): branch-free PGS row update (bit-identical results; 0 = the plain form everywhere)
   int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list
   int bfsBlocks = 0, colorBlocks = 0;
   DevBuf<int> colorCtl;

@@ -258,7 +258,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   unsigned long long is0[8] = {0, 0, 0, 0, 0, 0, (unsigned long long)nScenes, 0};
   CK(cudaMemcpyAsync(c->iterState.p, is0, sizeof(is0), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemsetAsync(c->sceneState.p, 0, (2 + MV_SLOTS) * (size_t)nScenes * sizeof(int), c->stream));
-  PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold, nScenes, sweep ? 0 : 1};
+  PgsParams PP{sweep ? 1.0 : P.omega, P.enable_compliance ? P.compliance : 0.0, sweep ? 1e-5 : P.tolerance, P.sliding_threshold, nScenes, sweep ? 0 : 1, c->fastRows};
   int iterations = sweep ? P.iterations_in_collection : P.iterations;
   CK(cudaEventRecord(c->ev[sweep ? 8 : 10], c->stream));
   // many small colours (hubs, batched scenes): one cooperative launch with grid barriers; few large colours: one

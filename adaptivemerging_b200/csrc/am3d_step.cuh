@@ -1058,6 +1058,7 @@ struct PgsParams {
   double omega, compliance, tolerance, sliding;
   int nScenes;  // sceneState = done[nScenes] | iterations[nScenes] | moving[nScenes][MV_SLOTS]
   int check;    // take the tolerance exit (full solve) or not (single sweep)
+  int fastRows; // branch-free row update where it applies (option "pgs_fast_rows", default on; results are identical)
 };
 
 __device__ __forceinline__ double dot6(const d3& jv, const d3& jw, const double* dvp) {
@@ -1099,6 +1100,43 @@ __device__ __forceinline__ double divExact(double a, double b, double y) {
   if (!(m > 1e-280 && m < 1e280)) q = a / b;
   return q;
 }
+// --- branch-free forms of the row update, for the latency-bound chain ---
+// Measured on B200 (tools/micro/fp64_latency.cu): a dependent DADD / DMUL / DFMA costs ~8.2 cycles, but fmax / fmin on
+// doubles compile to DSETP + selects behind a NaN branch (~26 cycles each), and every branch on a DSETP result (the zero
+// and range tests of divExact) stalls the in-order warp for the compare's latency.  The chain of a giant pair has nothing
+// to overlap with, so its row update is written without any compare-and-branch: the quotient is the Markstein sequence
+// unconditionally, the clamps are integer selects on the bit patterns, and the conditions under which those forms are not
+// the reference's arithmetic (quotient outside [2^-929, 2^930] - this includes 0, denormals, Inf, NaN - or a friction
+// bound that is not a non-negative finite number) only set a flag OFF the chain; a batch of 32 contacts that raised the
+// flag is run again from its saved deltaV with the exact (branching) forms.  Results are bit-identical either way.
+__device__ __forceinline__ double quotFast(double a, double b, double y, unsigned& bad) {
+  double q0 = a * y;
+  double r = __fma_rn(-b, q0, a);
+  double q = __fma_rn(r, y, q0);
+  r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, y, q);
+  // a == +-0: the quotient is a * y (a signed zero); the fused steps would lose the sign of -0
+  int ah = __double2hiint(a), al = __double2loint(a);
+  bool azero = (((unsigned)ah << 1) | (unsigned)al) == 0u;
+  unsigned e = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;
+  bad |= (!azero && (e - 94u > 1859u)) ? 1u : 0u;
+  return __hiloint2double(azero ? __double2hiint(q0) : __double2hiint(q), azero ? __double2loint(q0) : __double2loint(q));
+}
+// std::max(0.0, l) for a non-NaN l (PGS.java:120; -0.0 gives +0.0 as Math.max does)
+__device__ __forceinline__ double clampNonNegBits(double l) {
+  int hi = __double2hiint(l), lo = __double2loint(l);
+  bool neg = hi < 0;
+  return __hiloint2double(neg ? 0 : hi, neg ? 0 : lo);
+}
+// std::min(std::max(l, -limit), limit) for a finite limit >= +0 and a non-NaN l (PGS.java:151-154, 168-171): non-negative
+// doubles order like their bit patterns
+__device__ __forceinline__ double clampAbsBits(double l, double limit, unsigned& bad) {
+  unsigned long long ul = (unsigned long long)__double_as_longlong(limit), uq = (unsigned long long)__double_as_longlong(l);
+  bad |= (ul >= 0x7ff0000000000000ULL) ? 1u : 0u;  // negative, -0, Inf or NaN bound: take the exact path
+  bool gt = (uq & 0x7fffffffffffffffULL) > ul;
+  return __longlong_as_double((long long)(gt ? (ul | (uq & 0x8000000000000000ULL)) : uq));
+}
+
 // The tolerance exit of PGS.java:190-192 is taken PER SCENE: a context can hold many independent scenes (batched
 // copies), and each of them leaves the iteration when ITS largest |delta lambda| falls below the tolerance, exactly as
 // if it were solved alone.  A group whose |delta lambda| stays at or above the tolerance marks its scene as moving;
@@ -1130,6 +1168,19 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
   int fl = S.sgFlags[p];
   bool clamp = fl & SG_CLAMP;
   const bool hubA = HUB && (fl & SG_HUB1), hubB = HUB && (fl & SG_HUB2);  // HUB = false: the solve has no hub body
+  // branch-free rows: for clamped groups (no active magnet); a pinned side then carries a zeroed mass packet so that the
+  // unguarded update leaves its (never stored) deltaV at +0
+  const bool useFast = MODE == 1 && P.fastRows && clamp;
+  if (useFast) {
+    if (a < 0) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) M[k] = 0.0;
+    }
+    if (b < 0) {
+#pragma unroll
+      for (int k = 10; k < 20; k++) M[k] = 0.0;
+    }
+  }
   double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
   for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
@@ -1177,27 +1228,64 @@ __device__ __forceinline__ void pgsGroup(int p, const SolveArrays& S, double* __
       double den[3], y[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) { den[k] = DD[k] + P.compliance; y[k] = 1.0 / den[k]; }  // off the dependent chain
+      bool redo = true;
+      if (useFast) {
+        // branch-free rows (quotFast / clamp*Bits above) on a COPY of the two deltaV; a contact that raised the flag
+        // (quotient outside the normal range, bound not a finite non-negative number) is done again below, exactly
+        double f1[6], f2[6], g1[6], g2[6], lf[3], dmax = 0;
+        unsigned bad = 0;
+        unsigned long long mb = 0;
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
-        double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
-        double prev = lam[k];
-        double l = divExact(DD[k] * prev - P.omega * (bb[k] + Jdv), den[k], y[k]);
-        if (clamp) {
-          if (k == 0) l = fmax(0.0, l);
-          else {
-            double limit = mu * lam[0];
-            l = fmax(l, -limit);
-            l = fmin(l, limit);
-          }
+        for (int k = 0; k < 6; k++) { f1[k] = dv1[k]; f2[k] = dv2[k]; g1[k] = acc1[k]; g2[k] = acc2[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+          double Jdv = dot6(jav, jaw, f1) + dot6(dir[k], jbw, f2);
+          double l = quotFast(DD[k] * lam[k] - P.omega * (bb[k] + Jdv), den[k], y[k], bad);
+          l = (k == 0) ? clampNonNegBits(l) : clampAbsBits(l, mu * lf[0], bad);
+          lf[k] = l;
+          double diff = l - lam[k];
+          applyRow(f1, M[0], M + 1, jav, jaw, diff);   // (a pinned side has a zeroed mass packet: its copy stays +0)
+          applyRow(f2, M[10], M + 11, dir[k], jbw, diff);
+          if (hubA) applyRow(g1, M[0], M + 1, jav, jaw, diff);
+          if (hubB) applyRow(g2, M[10], M + 11, dir[k], jbw, diff);
+          unsigned long long db = (unsigned long long)__double_as_longlong(diff) & 0x7fffffffffffffffULL;
+          mb = db > mb ? db : mb;
         }
-        lam[k] = l;
-        double diff = l - prev;
-        if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
-        if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
-        if (hubA) applyRow(acc1, M[0], M + 1, jav, jaw, diff);
-        if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, diff);
-        localMax = fmax(localMax, fabs(diff));
+        dmax = __longlong_as_double((long long)mb);
+        if (!bad) {
+          redo = false;
+#pragma unroll
+          for (int k = 0; k < 6; k++) { dv1[k] = f1[k]; dv2[k] = f2[k]; acc1[k] = g1[k]; acc2[k] = g2[k]; }
+#pragma unroll
+          for (int k = 0; k < 3; k++) lam[k] = lf[k];
+          unsigned long long lb = (unsigned long long)__double_as_longlong(localMax);  // localMax >= 0 or NaN: bit patterns order
+          localMax = mb > lb ? dmax : localMax;
+        }
+      }
+      if (redo) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          d3 jav = vscale(-1, dir[k]), jaw = vcross(dir[k], r1), jbw = vcross(r2, dir[k]);
+          double Jdv = dot6(jav, jaw, dv1) + dot6(dir[k], jbw, dv2);
+          double prev = lam[k];
+          double l = divExact(DD[k] * prev - P.omega * (bb[k] + Jdv), den[k], y[k]);
+          if (clamp) {
+            if (k == 0) l = fmax(0.0, l);
+            else {
+              double limit = mu * lam[0];
+              l = fmax(l, -limit);
+              l = fmin(l, limit);
+            }
+          }
+          lam[k] = l;
+          double diff = l - prev;
+          if (a >= 0) applyRow(dv1, M[0], M + 1, jav, jaw, diff);
+          if (b >= 0) applyRow(dv2, M[10], M + 11, dir[k], jbw, diff);
+          if (hubA) applyRow(acc1, M[0], M + 1, jav, jaw, diff);
+          if (hubB) applyRow(acc2, M[10], M + 11, dir[k], jbw, diff);
+          localMax = fmax(localMax, fabs(diff));
+        }
       }
       st4(PK + 20, DD[2], lam[0], lam[1], lam[2]);
       if (lastIter) {
@@ -1283,6 +1371,98 @@ __device__ __forceinline__ void sceneIterEnd(int s, const PgsParams& P, int* __r
 #define GIANT_MIN 65       // contacts from which a group is solved by a warp
 #define GIANT_ROW 60       // doubles per prepared contact
 #define GIANT_WARPS 4      // warps per CTA of k_pgs_giant
+// the chain over one prepared batch (<= 32 contacts in W): every lane runs it (uniform), lane c keeps contact c's results.
+// FAST: branch-free row update, returns nonzero if the batch has to be run again with FAST = false.
+template <int MODE, bool HUB, bool FAST>
+__device__ __forceinline__ unsigned giantChain(const double* __restrict__ W, int n, int lane, bool hasA, bool hasB, bool hubA, bool hubB,
+                                               bool clamp, double mu, const double (&M)[20], const PgsParams& P, int lastIter,
+                                               double (&dv1)[8], double (&dv2)[8], double (&acc1)[6], double (&acc2)[6],
+                                               double& localMax, double (&myLam)[3], double& myD2, int& mySt) {
+  unsigned bad = 0;
+  unsigned long long maxBits = (unsigned long long)__double_as_longlong(localMax);  // (FAST) |diff| maximum as a bit pattern: NaN stays on top
+  for (int c = 0; c < n; c++) {
+    const double* R = W + c * GIANT_ROW;
+    double lam[3] = {R[57], R[58], R[59]};
+    double w12[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
+      d3 jav = vscale(-1, dir);
+      d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
+      d3 ta = {R[27 + 3 * k], R[28 + 3 * k], R[29 + 3 * k]}, tb = {R[36 + 3 * k], R[37 + 3 * k], R[38 + 3 * k]};
+      double diff;
+      if (MODE == 0) diff = lam[k];
+      else {
+        double Jdv = dot6(jav, jaw, dv1) + dot6(dir, jbw, dv2);
+        double prev = lam[k];
+        double num = R[48 + k] * prev - P.omega * (R[45 + k] + Jdv);
+        double l;
+        if (FAST) {
+          l = quotFast(num, R[51 + k], R[54 + k], bad);
+          l = (k == 0) ? clampNonNegBits(l) : clampAbsBits(l, mu * lam[0], bad);  // (the caller takes FAST only for clamped groups)
+        } else {
+          l = divExact(num, R[51 + k], R[54 + k]);
+          if (clamp) {
+            if (k == 0) l = fmax(0.0, l);
+            else {
+              double limit = mu * lam[0];
+              l = fmax(l, -limit);
+              l = fmin(l, limit);
+            }
+          }
+        }
+        lam[k] = l;
+        diff = l - prev;
+        if (FAST) {
+          unsigned long long db = (unsigned long long)__double_as_longlong(diff) & 0x7fffffffffffffffULL;
+          maxBits = db > maxBits ? db : maxBits;
+        } else {
+          localMax = fmax(localMax, fabs(diff));
+        }
+      }
+      // PGS.updateDeltaVwithLambdai :221-245 with jinv * (angular half) taken from the prepared row.
+      // FAST: no test on the body - the prepared rows of a pinned side carry jinv * (angular half) = 0 and its inverse mass
+      // is passed as 0, so its deltaV stays +0 exactly as when the update is skipped.
+      if (FAST || hasA) {
+        double s1 = M[0] * diff;
+        dv1[0] = s1 * jav.x + dv1[0]; dv1[1] = s1 * jav.y + dv1[1]; dv1[2] = s1 * jav.z + dv1[2];
+        dv1[3] = diff * ta.x + dv1[3]; dv1[4] = diff * ta.y + dv1[4]; dv1[5] = diff * ta.z + dv1[5];
+        if (hubA) {
+          acc1[0] = s1 * jav.x + acc1[0]; acc1[1] = s1 * jav.y + acc1[1]; acc1[2] = s1 * jav.z + acc1[2];
+          acc1[3] = diff * ta.x + acc1[3]; acc1[4] = diff * ta.y + acc1[4]; acc1[5] = diff * ta.z + acc1[5];
+        }
+      }
+      if (FAST || hasB) {
+        double s2 = M[10] * diff;
+        dv2[0] = s2 * dir.x + dv2[0]; dv2[1] = s2 * dir.y + dv2[1]; dv2[2] = s2 * dir.z + dv2[2];
+        dv2[3] = diff * tb.x + dv2[3]; dv2[4] = diff * tb.y + dv2[4]; dv2[5] = diff * tb.z + dv2[5];
+        if (hubB) {
+          acc2[0] = s2 * dir.x + acc2[0]; acc2[1] = s2 * dir.y + acc2[1]; acc2[2] = s2 * dir.z + acc2[2];
+          acc2[3] = diff * tb.x + acc2[3]; acc2[4] = diff * tb.y + acc2[4]; acc2[5] = diff * tb.z + acc2[5];
+        }
+      }
+    }
+    if (MODE == 1) {
+      int st = 0;
+      if (lastIter) {  // Contact.updateContactState :385-398, with the deltaV after this contact's three rows
+#pragma unroll
+        for (int k = 1; k < 3; k++) {
+          d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
+          d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
+          w12[k - 1] = R[45 + k] + (dot6(vscale(-1, dir), jaw, dv1) + dot6(dir, jbw, dv2));
+        }
+        if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
+        else if (fabs(w12[0]) > P.sliding) st = AM3D_CS_ONEDGE;
+        else if (fabs(w12[1]) > P.sliding) st = AM3D_CS_ONEDGE;
+        else st = AM3D_CS_CLEAR;
+      }
+      if (lane == c) { myLam[0] = lam[0]; myLam[1] = lam[1]; myLam[2] = lam[2]; myD2 = R[50]; mySt = st; }
+    }
+  }
+  if (FAST && MODE == 1) localMax = __longlong_as_double((long long)maxBits);
+  return bad;
+}
+
 template <int MODE, bool HUB>
 __global__ void __launch_bounds__(32 * GIANT_WARPS)
 k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
@@ -1308,6 +1488,16 @@ k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
   const int fl = S.sgFlags[p];
   const bool clamp = fl & SG_CLAMP;
   const bool hubA = HUB && (fl & SG_HUB1), hubB = HUB && (fl & SG_HUB2);
+  // a pinned side (index < 0) is never updated: with its inverse mass and inertia zeroed the unguarded update of the
+  // branch-free chain adds +-0 to a deltaV that is +0 (the guarded form reads M only where the side is not pinned)
+  if (a < 0) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) M[k] = 0.0;
+  }
+  if (b < 0) {
+#pragma unroll
+    for (int k = 10; k < 20; k++) M[k] = 0.0;
+  }
   double dv1[8], dv2[8], acc1[6], acc2[6];
 #pragma unroll
   for (int k = 0; k < 8; k++) { dv1[k] = 0.0; dv2[k] = 0.0; }
@@ -1350,73 +1540,25 @@ k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
       }
     }
     __syncwarp();
-    // ---- chain: every lane runs it (uniform), lane c keeps contact c's results ----
+    // ---- chain ----
     double myLam[3] = {0, 0, 0}, myD2 = 0;
     int mySt = 0;
-    for (int c = 0; c < n; c++) {
-      const double* R = W + c * GIANT_ROW;
-      double lam[3] = {R[57], R[58], R[59]};
-      double w12[2] = {0, 0};
+    if (MODE == 1 && clamp && P.fastRows) {  // (unclamped = a contact with an active magnet, PGS.java:119: exact forms)
+      double sv1[6], sv2[6], sa1[6], sa2[6], sMax = localMax;  // state at the start of the batch, for the exact re-run
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
-        d3 jav = vscale(-1, dir);
-        d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
-        d3 ta = {R[27 + 3 * k], R[28 + 3 * k], R[29 + 3 * k]}, tb = {R[36 + 3 * k], R[37 + 3 * k], R[38 + 3 * k]};
-        double diff;
-        if (MODE == 0) diff = lam[k];
-        else {
-          double Jdv = dot6(jav, jaw, dv1) + dot6(dir, jbw, dv2);
-          double prev = lam[k];
-          double l = divExact(R[48 + k] * prev - P.omega * (R[45 + k] + Jdv), R[51 + k], R[54 + k]);
-          if (clamp) {
-            if (k == 0) l = fmax(0.0, l);
-            else {
-              double limit = mu * lam[0];
-              l = fmax(l, -limit);
-              l = fmin(l, limit);
-            }
-          }
-          lam[k] = l;
-          diff = l - prev;
-          localMax = fmax(localMax, fabs(diff));
-        }
-        // PGS.updateDeltaVwithLambdai :221-245 with jinv * (angular half) taken from the prepared row
-        if (a >= 0) {
-          double s1 = M[0] * diff;
-          dv1[0] = s1 * jav.x + dv1[0]; dv1[1] = s1 * jav.y + dv1[1]; dv1[2] = s1 * jav.z + dv1[2];
-          dv1[3] = diff * ta.x + dv1[3]; dv1[4] = diff * ta.y + dv1[4]; dv1[5] = diff * ta.z + dv1[5];
-          if (hubA) {
-            acc1[0] = s1 * jav.x + acc1[0]; acc1[1] = s1 * jav.y + acc1[1]; acc1[2] = s1 * jav.z + acc1[2];
-            acc1[3] = diff * ta.x + acc1[3]; acc1[4] = diff * ta.y + acc1[4]; acc1[5] = diff * ta.z + acc1[5];
-          }
-        }
-        if (b >= 0) {
-          double s2 = M[10] * diff;
-          dv2[0] = s2 * dir.x + dv2[0]; dv2[1] = s2 * dir.y + dv2[1]; dv2[2] = s2 * dir.z + dv2[2];
-          dv2[3] = diff * tb.x + dv2[3]; dv2[4] = diff * tb.y + dv2[4]; dv2[5] = diff * tb.z + dv2[5];
-          if (hubB) {
-            acc2[0] = s2 * dir.x + acc2[0]; acc2[1] = s2 * dir.y + acc2[1]; acc2[2] = s2 * dir.z + acc2[2];
-            acc2[3] = diff * tb.x + acc2[3]; acc2[4] = diff * tb.y + acc2[4]; acc2[5] = diff * tb.z + acc2[5];
-          }
-        }
-      }
-      if (MODE == 1) {
-        int st = 0;
-        if (lastIter) {  // Contact.updateContactState :385-398, with the deltaV after this contact's three rows
+      for (int k = 0; k < 6; k++) { sv1[k] = dv1[k]; sv2[k] = dv2[k]; sa1[k] = acc1[k]; sa2[k] = acc2[k]; }
+      unsigned bad = giantChain<MODE, HUB, true>(W, n, lane, a >= 0, b >= 0, hubA, hubB, clamp, mu, M, P, lastIter, dv1, dv2, acc1, acc2,
+                                                 localMax, myLam, myD2, mySt);
+      if (bad) {  // (uniform: every lane ran the same chain)
 #pragma unroll
-          for (int k = 1; k < 3; k++) {
-            d3 dir = {R[3 * k], R[3 * k + 1], R[3 * k + 2]};
-            d3 jaw = {R[9 + 3 * k], R[10 + 3 * k], R[11 + 3 * k]}, jbw = {R[18 + 3 * k], R[19 + 3 * k], R[20 + 3 * k]};
-            w12[k - 1] = R[45 + k] + (dot6(vscale(-1, dir), jaw, dv1) + dot6(dir, jbw, dv2));
-          }
-          if (fabs(lam[0]) <= 1e-14) st = AM3D_CS_BROKEN;
-          else if (fabs(w12[0]) > P.sliding) st = AM3D_CS_ONEDGE;
-          else if (fabs(w12[1]) > P.sliding) st = AM3D_CS_ONEDGE;
-          else st = AM3D_CS_CLEAR;
-        }
-        if (lane == c) { myLam[0] = lam[0]; myLam[1] = lam[1]; myLam[2] = lam[2]; myD2 = R[50]; mySt = st; }
+        for (int k = 0; k < 6; k++) { dv1[k] = sv1[k]; dv2[k] = sv2[k]; acc1[k] = sa1[k]; acc2[k] = sa2[k]; }
+        localMax = sMax;
+        giantChain<MODE, HUB, false>(W, n, lane, a >= 0, b >= 0, hubA, hubB, clamp, mu, M, P, lastIter, dv1, dv2, acc1, acc2, localMax,
+                                     myLam, myD2, mySt);
       }
+    } else {
+      giantChain<MODE, HUB, false>(W, n, lane, a >= 0, b >= 0, hubA, hubB, clamp, mu, M, P, lastIter, dv1, dv2, acc1, acc2, localMax,
+                                   myLam, myD2, mySt);
     }
     if (MODE == 1 && lane < n) {
       st4(PK + 20, myD2, myLam[0], myLam[1], myLam[2]);

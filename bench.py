@@ -190,6 +190,8 @@ def run_leg(local, blob, params, steps, warmup, settle, with_e2e, barrier):
     from adaptivemerging_b200.system import RigidBodySystem
     sysm = RigidBodySystem(local).load(blob, params)
     sysm.set_option("record_events", 0)  # the merge / unmerge event log is a parity-test aid
+    for kv in filter(None, os.environ.get("AM3D_OPTIONS", "").split(",")):  # A/B runs: AM3D_OPTIONS=pgs_fast_rows=0,...
+        sysm.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     for _ in range(settle + warmup):
         sysm.advanceTime(0.05)
     s0 = sysm.stats()

@@ -60,7 +60,7 @@ def test_collection_collision_modes_give_the_same_run():
     assert len(runs[0][1]) > 0
     for b, ev, nc in runs[1:]:
         assert ev == runs[0][1] and nc == runs[0][2]
-        for k in ("x", "R", "v", "w"):
+        for k in ("x", "R", "v", "omega"):
             assert np.array_equal(b[k], runs[0][0][k]), k
 
 
