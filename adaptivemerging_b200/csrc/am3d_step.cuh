@@ -1463,6 +1463,36 @@ __device__ __forceinline__ unsigned giantChain(const double* __restrict__ W, int
   return bad;
 }
 
+// prepare one contact of a giant group: everything of its three rows that does not depend on deltaV, into 60 doubles
+__device__ __forceinline__ void giantPrepare(const double* __restrict__ PK, double* __restrict__ R, const double (&M)[20], double compliance) {
+  double Q[24];
+#pragma unroll
+  for (int k = 0; k < 6; k++) ld4(PK + 4 * k, Q + 4 * k);
+  d3 r1 = {Q[9], Q[10], Q[11]}, r2 = {Q[12], Q[13], Q[14]};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    d3 dir = {Q[3 * k], Q[3 * k + 1], Q[3 * k + 2]};
+    d3 jaw = vcross(dir, r1), jbw = vcross(r2, dir);
+    R[3 * k] = dir.x; R[3 * k + 1] = dir.y; R[3 * k + 2] = dir.z;
+    R[9 + 3 * k] = jaw.x; R[10 + 3 * k] = jaw.y; R[11 + 3 * k] = jaw.z;
+    R[18 + 3 * k] = jbw.x; R[19 + 3 * k] = jbw.y; R[20 + 3 * k] = jbw.z;
+    const double* J1 = M + 1;
+    const double* J2 = M + 11;
+    R[27 + 3 * k] = J1[0] * jaw.x + J1[1] * jaw.y + J1[2] * jaw.z;
+    R[28 + 3 * k] = J1[3] * jaw.x + J1[4] * jaw.y + J1[5] * jaw.z;
+    R[29 + 3 * k] = J1[6] * jaw.x + J1[7] * jaw.y + J1[8] * jaw.z;
+    R[36 + 3 * k] = J2[0] * jbw.x + J2[1] * jbw.y + J2[2] * jbw.z;
+    R[37 + 3 * k] = J2[3] * jbw.x + J2[4] * jbw.y + J2[5] * jbw.z;
+    R[38 + 3 * k] = J2[6] * jbw.x + J2[7] * jbw.y + J2[8] * jbw.z;
+    R[45 + k] = Q[15 + k];                      // b
+    R[48 + k] = Q[18 + k];                      // D
+    double den = Q[18 + k] + compliance;
+    R[51 + k] = den;
+    R[54 + k] = 1.0 / den;
+    R[57 + k] = Q[21 + k];                      // lambda
+  }
+}
+
 template <int MODE, bool HUB>
 __global__ void __launch_bounds__(32 * GIANT_WARPS)
 k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
@@ -1510,35 +1540,7 @@ k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
     const int n = min(32, cnt - base);
     double* PK = S.scP + 24 * (size_t)(start + base + lane);
     // ---- prepare: lane i -> contact base + i ----
-    if (lane < n) {
-      double Q[24];
-#pragma unroll
-      for (int k = 0; k < 6; k++) ld4(PK + 4 * k, Q + 4 * k);
-      double* R = W + lane * GIANT_ROW;
-      d3 r1 = {Q[9], Q[10], Q[11]}, r2 = {Q[12], Q[13], Q[14]};
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        d3 dir = {Q[3 * k], Q[3 * k + 1], Q[3 * k + 2]};
-        d3 jaw = vcross(dir, r1), jbw = vcross(r2, dir);
-        R[3 * k] = dir.x; R[3 * k + 1] = dir.y; R[3 * k + 2] = dir.z;
-        R[9 + 3 * k] = jaw.x; R[10 + 3 * k] = jaw.y; R[11 + 3 * k] = jaw.z;
-        R[18 + 3 * k] = jbw.x; R[19 + 3 * k] = jbw.y; R[20 + 3 * k] = jbw.z;
-        const double* J1 = M + 1;
-        const double* J2 = M + 11;
-        R[27 + 3 * k] = J1[0] * jaw.x + J1[1] * jaw.y + J1[2] * jaw.z;
-        R[28 + 3 * k] = J1[3] * jaw.x + J1[4] * jaw.y + J1[5] * jaw.z;
-        R[29 + 3 * k] = J1[6] * jaw.x + J1[7] * jaw.y + J1[8] * jaw.z;
-        R[36 + 3 * k] = J2[0] * jbw.x + J2[1] * jbw.y + J2[2] * jbw.z;
-        R[37 + 3 * k] = J2[3] * jbw.x + J2[4] * jbw.y + J2[5] * jbw.z;
-        R[38 + 3 * k] = J2[6] * jbw.x + J2[7] * jbw.y + J2[8] * jbw.z;
-        R[45 + k] = Q[15 + k];                      // b
-        R[48 + k] = Q[18 + k];                      // D
-        double den = Q[18 + k] + P.compliance;
-        R[51 + k] = den;
-        R[54 + k] = 1.0 / den;
-        R[57 + k] = Q[21 + k];                      // lambda
-      }
-    }
+    if (lane < n) giantPrepare(PK, W + lane * GIANT_ROW, M, P.compliance);
     __syncwarp();
     // ---- chain ----
     double myLam[3] = {0, 0, 0}, myD2 = 0;
@@ -1591,6 +1593,9 @@ k_pgs_giant(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
     }
   }
 }
+// (Measured and not kept, round 2: a producer warp preparing batch k + 1 into a second shared-memory buffer while a consumer
+// warp walks the chain of batch k - no gain: the preparation is ~10 % of a batch; the chain, ~300 instructions per contact of
+// which 183 are FP64 at 2 cycles of the pipe each and ~150 cycles per row are a dependent sequence, is what a launch costs.)
 // giant groups per phase (they lead their phase: groups are sorted by descending contact count)
 __global__ void k_phase_giants(int ng, const int* __restrict__ sgCount, const int* __restrict__ phaseOf, int* __restrict__ phaseGiants) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
