@@ -175,6 +175,13 @@ static void postStabilization(am3d_ctx* c, double dt) {
            c->jinv0.p, c->mA0.p, c->jinv.p, c->mA.p);
 }
 
+// a velocity poke uploaded by am3d_add_velocities and not yet added to the velocities
+static void flushPokes(am3d_ctx* c) {
+  if (!c->pokesPending) return;
+  CK(cudaStreamWaitEvent(c->stream, c->evPoke, 0));
+  LAUNCH(c, k_add_velocities, nblk(c->NB), BLK, c->NB, c->parent.p, c->pokeV.p, c->pokeW.p, c->v.p, c->w.p);
+  c->pokesPending = false;
+}
 static void stepOnce(am3d_ctx* c, double dt) {
   const am3d_params& P = c->P;
   int NS = c->NS, NB = c->NB;
@@ -182,11 +189,15 @@ static void stepOnce(am3d_ctx* c, double dt) {
   double theta = P.gravity_angle_deg / 180.0 * M_PI;
   double gx = P.gravity_amount * cos(theta), gy = P.gravity_amount * sin(theta);
   CK(cudaEventRecord(c->ev[0], c->stream));
-  applyExternalForces(c, dt);                   // clearBodies + applyExternalForces  (:108-116)
+  // a velocity poke still on its way up (am3d_add_velocities): detection reads positions only, so it goes first and the
+  // poke + the external forces (springs read velocities) follow it - the same values as in the reference's order
+  const bool pokeLate = c->pokesPending;
+  if (!pokeLate) applyExternalForces(c, dt);    // clearBodies + applyExternalForces  (:108-116)
   CK(cudaEventRecord(c->ev[1], c->stream));
   detect(c);                                    // updateContactsMap + collisionDetection (:119-120)
   buildBodyPairs(c);                            // updateBodyPairContacts (:121)
   CK(cudaEventRecord(c->ev[2], c->stream));
+  if (pokeLate) { flushPokes(c); applyExternalForces(c, dt); }
   warmStart(c);                                 // warmStart(false) (:124)
   CK(cudaEventRecord(c->ev[3], c->stream));
   if (P.enable_sleeping) {                      // sleeping.wake() (:128)
@@ -290,13 +301,17 @@ static void waitPending(am3d_ctx* c) {
     if (rc != AM3D_OK && c->asyncStatus == AM3D_OK) c->asyncStatus = rc;
   }
 }
-#define API_BEGIN(ctx)                      \
+// (_NOFLUSH: the entry points that leave an uploaded velocity poke pending, see am3d_add_velocities)
+#define API_BEGIN_NOFLUSH(ctx)              \
   if (!(ctx)) return AM3D_EINVAL;           \
   try {                                     \
     waitPending(ctx);                       \
     cudaSetDevice((ctx)->device);           \
     amCurrentStream() = (ctx)->stream;      \
     amCurrentPool() = (ctx)->pool;
+#define API_BEGIN(ctx)                      \
+  API_BEGIN_NOFLUSH(ctx)                    \
+    if ((ctx)->pokesPending) flushPokes(ctx);
 #define API_END(ctx)                        \
     return AM3D_OK;                         \
   } catch (const AmError& e) {              \
@@ -421,7 +436,11 @@ int am3d_destroy(am3d_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->evCreated) for (int i = 0; i < 24; i++) cudaEventDestroy(c->ev[i]);
+  if (c->mappedHost) cudaFreeHost(c->mappedHost);
   if (c->copyStream) {
+    if (c->upStream) { cudaStreamSynchronize(c->upStream); cudaStreamDestroy(c->upStream); }
+    if (c->evPoke) cudaEventDestroy(c->evPoke);
+    if (c->evMain) cudaEventDestroy(c->evMain);
     cudaStreamSynchronize(c->copyStream);
     cudaEventDestroy(c->evSnap); cudaEventDestroy(c->evCopied);
     cudaStreamDestroy(c->copyStream);
@@ -475,7 +494,7 @@ int am3d_reset(am3d_ctx* c) {
 }
 
 int am3d_step(am3d_ctx* c, double dt, int nsteps) {
-  API_BEGIN(c)
+  API_BEGIN_NOFLUSH(c)
   if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
   for (int i = 0; i < nsteps; i++) stepOnce(c, dt);
   API_END(c)
@@ -496,7 +515,7 @@ static int stepBody(am3d_ctx* c, double dt, int nsteps) {
   }
 }
 int am3d_step_async(am3d_ctx* c, double dt, int nsteps) {
-  API_BEGIN(c)  // waits for steps still pending from an earlier call
+  API_BEGIN_NOFLUSH(c)  // waits for steps still pending from an earlier call
   if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
   if (c->asyncStatus != AM3D_OK) { int rc = c->asyncStatus; c->asyncStatus = AM3D_OK; return rc; }
   c->pending = std::async(std::launch::async, stepBody, c, dt, nsteps);
@@ -524,14 +543,20 @@ __global__ void k_body_flags_out(int nb, const int* __restrict__ parent, const i
   sleeping[i] = ((flags[t] & AM3D_F_SLEEPING) && !(flags[t] & AM3D_F_DORMANT)) ? 1 : 0;  // (dormant bodies carry the flag only to stay out of the integrator)
   collection[i] = p >= 0 ? p - nb : -1;
 }
-static void downloadBodies(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
-  if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
-  size_t nb = c->NB;
+static void ensureCopyStream(am3d_ctx* c) {
   if (!c->copyStream) {
     CK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->evSnap, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->upStream, cudaStreamNonBlocking));  // (uploads on their own stream: the two directions use different copy engines)
+    CK(cudaEventCreateWithFlags(&c->evPoke, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->evMain, cudaEventDisableTiming));
   }
+}
+static void downloadBodies(am3d_ctx* c, double* x, double* R, double* v, double* omega, int32_t* sleeping, int32_t* collection) {
+  if (!c->haveScene) throw AmError(AM3D_ESTATE, "no scene uploaded");
+  size_t nb = c->NB;
+  ensureCopyStream(c);
   if (c->copyPending) { CK(cudaEventSynchronize(c->evCopied)); c->copyPending = false; }  // staging is free again
   c->stD.ensure(18 * nb + 8); c->stI.ensure(2 * nb + 8);
   double *sx = c->stD.p, *sR = sx + 3 * nb, *sv = sR + 9 * nb, *sw = sv + 3 * nb;
@@ -717,14 +742,23 @@ int am3d_apply_impulse(am3d_ctx* c, int body, const double pickedPointB[3], cons
   API_END(c)
 }
 
+// The per-body pokes travel on an upload stream and are added to the velocities by the NEXT step after its contact
+// detection - detection reads positions only, so the upload (48 B per body) runs beside it instead of in front of the step -
+// or by whatever entry point is called first (every other call flushes a pending poke, so velocities read back or written
+// in between see it applied).  The host buffers must stay untouched until that step (or call) has returned, as with any
+// cudaMemcpyAsync from pinned memory.
 int am3d_add_velocities(am3d_ctx* c, const double* dv, const double* domega) {
-  API_BEGIN(c)
+  API_BEGIN(c)   // (a poke still pending from an earlier call is applied first)
   if (!c->haveScene || !dv || !domega) throw AmError(AM3D_EINVAL, "no scene / null buffers");
   int nb = c->NB;
+  ensureCopyStream(c);
   c->pokeV.ensure(3 * (size_t)nb); c->pokeW.ensure(3 * (size_t)nb);
-  CK(cudaMemcpyAsync(c->pokeV.p, dv, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->pokeW.p, domega, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  LAUNCH(c, k_add_velocities, nblk(nb), BLK, nb, c->parent.p, c->pokeV.p, c->pokeW.p, c->v.p, c->w.p);
+  CK(cudaEventRecord(c->evMain, c->stream));             // the staging buffers exist / were read by the last poke
+  CK(cudaStreamWaitEvent(c->upStream, c->evMain, 0));
+  CK(cudaMemcpyAsync(c->pokeV.p, dv, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->upStream));
+  CK(cudaMemcpyAsync(c->pokeW.p, domega, 3 * (size_t)nb * sizeof(double), cudaMemcpyHostToDevice, c->upStream));
+  CK(cudaEventRecord(c->evPoke, c->upStream));
+  c->pokesPending = true;
   API_END(c)
 }
 

@@ -281,6 +281,11 @@ struct am3d_ctx {
   // ---- timing --------------------------------------------------------------------------------------
   am3d_timings T;
   cudaEvent_t ev[24];
+  cudaEvent_t evPoke = nullptr, evMain = nullptr;  // velocity pokes uploaded on the copy stream (am3d_add_velocities)
+  bool pokesPending = false;
+  int* mappedHost = nullptr;   // mapped pinned memory for the small read-backs of a step (readBack in am3d_host_util.cuh)
+  int* mappedDev = nullptr;
+  cudaStream_t upStream = nullptr;
   cudaStream_t copyStream = nullptr;  // device -> host copies of the body state run beside the next step
   cudaEvent_t evSnap = nullptr, evCopied = nullptr;
   bool copyPending = false;

@@ -45,8 +45,7 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
     CK(cudaLaunchCooperativeKernel((const void*)k_color_coop, dim3(blocks), dim3(256), args, 0, c->stream));
     c->kernelLaunches++;
     int out[2];
-    CK(cudaMemcpyAsync(out, c->colorCtl.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    readBack(c, out, c->colorCtl.p + 4, 2);
     if (out[1]) throw AmError(AM3D_ECAPACITY, "more than 4096 colours needed");
     page = out[0] - 1;
   }
@@ -74,8 +73,7 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   c->dColorStart.ensure(nPhases + 2);
   LAUNCH(c, k_phase_fill, nblk(ng), BLK, ng, c->phaseHead.p, c->phaseScan.p, c->dColorStart.p, c->sgPhase.p);
   c->colorStart.resize(nPhases + 1);
-  CK(cudaMemcpyAsync(c->colorStart.data(), c->dColorStart.p, (nPhases + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  readBack(c, c->colorStart.data(), c->dColorStart.p, (size_t)nPhases + 1);
   c->nColors = nPhases;
   c->nGroups = ng;
   if (c->nPart > 0) {
@@ -222,8 +220,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
            c->hubRunColor.p);
     CK(cudaMemcpyAsync(c->hubRunStart.p + nr, &c->nHubEntries, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     std::vector<int> rc(nr);
-    CK(cudaMemcpyAsync(rc.data(), c->hubRunColor.p, nr * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    readBack(c, rc.data(), c->hubRunColor.p, (size_t)nr);
     std::vector<int> perColor(c->nColors, 0);
     for (int r = 0; r < nr; r++) perColor[rc[r]]++;
     for (int k = 0; k < c->nColors; k++) c->colorRunStart[k + 1] = c->colorRunStart[k] + perColor[k];
@@ -250,8 +247,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
     c->phaseGiants.ensure(c->nColors + 1);
     CK(cudaMemsetAsync(c->phaseGiants.p, 0, (c->nColors + 1) * sizeof(int), c->stream));
     LAUNCH(c, k_phase_giants, nblk(ng), BLK, ng, c->sgCount.p, c->sgPhase.p, c->phaseGiants.p);
-    CK(cudaMemcpyAsync(giants.data(), c->phaseGiants.p, c->nColors * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    readBack(c, giants.data(), c->phaseGiants.p, (size_t)c->nColors);
     for (int g : giants) nGiants += g;
   }
   // iterState: [1] every scene done, [2] largest iteration count, [4] contact-iterations, [6] scenes still iterating
@@ -360,8 +356,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
   } else if (!sweep) {
     LAUNCH(c, k_row_updates, nblk(ng), BLK, ng, S, nScenes, c->iterState.p);
     unsigned long long st[5];
-    CK(cudaMemcpyAsync(st, c->iterState.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    readBack(c, st, c->iterState.p, sizeof(st) / sizeof(int));
     c->T.pgs_iterations = (int)st[2];
     c->T.pgs_colors = c->nColors;
     float ms = 0;

@@ -38,10 +38,36 @@ static void h2d(am3d_ctx* c, DevBuf<T>& d, const T* src, size_t n) {
 template <class T>
 static void h2dv(am3d_ctx* c, DevBuf<T>& d, const std::vector<T>& v) { h2d(c, d, v.data(), v.size()); }
 
+// Small read-backs of the step (scan totals, phase tables, iteration counts) do NOT go through the copy engine: a kernel
+// writes them into mapped pinned host memory.  A device-to-host memcpy - however small - queues behind whatever the
+// copy engine is moving, and with am3d_download_bodies_async that is the previous step's body state (150 - 200 MB): the
+// ~15 read-backs of a step then waited for it one after the other, which put the whole transfer (2.5 - 3 ms) back on
+// the step's critical path.
+#define AM3D_MAPPED_INTS 16384
+__global__ void k_export_ints(const int* __restrict__ src, int* __restrict__ dstMapped, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dstMapped[i] = src[i];
+}
+// n 32-bit words from device memory to `dst`, synchronising the context's stream
+static void readBack(am3d_ctx* c, void* dst, const void* devSrc, size_t words) {
+  if (words == 0) { CK(cudaStreamSynchronize(c->stream)); return; }
+  if (words > AM3D_MAPPED_INTS) {
+    CK(cudaMemcpyAsync(dst, devSrc, words * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return;
+  }
+  if (!c->mappedHost) {
+    CK(cudaHostAlloc((void**)&c->mappedHost, AM3D_MAPPED_INTS * sizeof(int), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c->mappedDev, c->mappedHost, 0));
+  }
+  int blocks = (int)std::min<size_t>((words + 255) / 256, 16);
+  k_export_ints<<<blocks, 256, 0, c->stream>>>((const int*)devSrc, c->mappedDev, (int)words);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  memcpy(dst, c->mappedHost, words * sizeof(int));
+}
 static int readInt(am3d_ctx* c, const int* p) {
   int v;
-  CK(cudaMemcpyAsync(&v, p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  readBack(c, &v, p, 1);
   return v;
 }
 

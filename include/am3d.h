@@ -311,7 +311,10 @@ int am3d_set_mouse_spring(am3d_ctx* ctx, int body, const double grabPointB[3], c
  * (or the re-application of the forces after a merge event) applies the stored force once more to the body alone, as
  * the reference does */
 int am3d_apply_impulse(am3d_ctx* ctx, int body, const double pickedPointB[3], const double endPointW[3], double scale);
-/* bulk version: per-body velocity increments [3n] each (zeros are skipped), added to the top-level entity */
+/* bulk version: per-body velocity increments [3n] each (zeros are skipped), added to the top-level entity.
+ * The two arrays are uploaded on a separate stream and added by the NEXT am3d_step after its contact detection (which
+ * reads positions only) - or by whichever other entry point is called first, so a read-back in between sees them applied.
+ * Keep the host arrays unchanged until that call has returned (pinned memory: the copy is asynchronous). */
 int am3d_add_velocities(am3d_ctx* ctx, const double* dv, const double* domega);
 int am3d_upload_bodies(am3d_ctx* ctx, const double* x, const double* R, const double* v,
                        const double* omega); /* teacher forcing: overwrite the state of all leaf bodies */

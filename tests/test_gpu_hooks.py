@@ -122,3 +122,32 @@ def test_magnet_holds_a_box_until_it_is_switched_off():
     # and with merging on: same events on both sides
     gpu, cpu, ev_g, ev_o, worst = lockstep(blob, params(), 120, tol=1e-6, script=script)
     assert ev_g == ev_o
+
+
+def test_velocity_pokes_uploaded_beside_detection_equal_per_body_writes():
+    """am3d_add_velocities: the per-body pokes go up on the copy stream and are applied by the next step after its
+    detection (or by the next call, whichever comes first) - the run equals one with the same pokes written body by body."""
+    blob = box_stack(3, 4, 3, pile=True)
+    nb = blob.n_bodies
+    rng = np.random.default_rng(11)
+    a = RigidBodySystem(0).load(blob, params())
+    b = RigidBodySystem(0).load(blob, params())
+    for step in range(60):
+        if step % 7 == 3:
+            dv = np.zeros((nb, 3)); dw = np.zeros((nb, 3))
+            for body in rng.choice(np.arange(1, nb), 3, replace=False):
+                dv[body] = rng.uniform(-0.3, 0.3, 3); dw[body] = rng.uniform(-0.2, 0.2, 3)
+            a.add_velocities(dv, dw)
+            if step == 10:   # read back before stepping: the pending poke is applied first
+                va = a.bodies()["v"].copy()
+            for body in np.nonzero(np.abs(dv).sum(1) + np.abs(dw).sum(1))[0]:
+                b.add_body_velocity(int(body), dv[body], dw[body])
+            if step == 10:
+                assert np.array_equal(va, b.bodies()["v"])
+        a.advanceTime(0.05)
+        b.advanceTime(0.05)
+    ga, gb = a.bodies(), b.bodies()
+    for k in ("x", "R", "v", "omega"):
+        assert np.array_equal(ga[k], gb[k]), k
+    assert a.events().tolist() == b.events().tolist()
+    a.close(); b.close()
