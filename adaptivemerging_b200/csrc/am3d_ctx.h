@@ -199,6 +199,8 @@ struct am3d_ctx {
   // raw hits (slot layout)
   DevBuf<double> hitPos, hitNrm, hitViol;
   DevBuf<int> treeList;  // indices of the candidate pairs that involve a sphere tree
+  DevBuf<unsigned long long> taskVal;  // tree x tree pairs split into one task per waiting node pair (k_tree_tasks)
+  DevBuf<int> taskPair, taskCount, taskPrefix, treePairStart, treePairN, treePairPrefix;
   DevBuf<int> hitMeta;  // [4]: info, bv1, bv2, leaf
   long long nSlots = 0;
 
@@ -243,6 +245,7 @@ struct am3d_ctx {
   int useClusters = 1, maxClusters = 0, nPart = 0, hPartScenes = 0;
   DevBuf<int> partRange, partSceneStart, partRemaining;
   std::vector<int> hPartSceneStart, hPartCount;
+  int treeSplit = 1;      // am3d_set_option("tree_split", 0/1): tree x tree pairs with a large frontier are split into one task per node pair
   int fastRows = 1;       // am3d_set_option("pgs_fast_rows", 0/1): branch-free PGS row update (bit-identical results; 0 = the plain form everywhere)
   int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list
   int bfsBlocks = 0, colorBlocks = 0;

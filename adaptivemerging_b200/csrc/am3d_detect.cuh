@@ -323,11 +323,80 @@ struct TreeCtx {
   const int* ndCount;
 };
 
+#define SPLIT_TARGET 64  // node pairs waiting at which a tree x tree pair is handed over to one warp per node pair
+struct TreeTasks {
+  unsigned long long* val;  // node pair (node of tree 1 << 32 | node of tree 2) a task starts from
+  int* pair;                // candidate pair it belongs to
+  int* count;               // contacts it found (count pass)
+  int* prefix;              // exclusive scan of count, [nTasks + 1]
+  int* counter;             // tasks allocated so far
+  int cap;
+  int target;               // node pairs waiting at which a pair is handed over (SPLIT_TARGET; a huge value = never)
+  int* pairStart;           // per candidate pair: its tasks [pairStart, pairStart + pairN) and the contacts of its own prefix walk
+  int* pairN;
+  int* pairPrefix;
+};
+
+// One step of the tree x tree descent (collideSphereTrees :975-1009): the children of the larger sphere of (n1, n2) -
+// of node2 when node1 is a leaf, of node1 when node2 is - are tested against the other node by the lanes; overlapping
+// pairs that are not leaf x leaf are pushed at stack[sp..], leaf x leaf contacts are counted (EMIT: written at base + count).
+template <bool EMIT>
+__device__ __forceinline__ void treeTreeStep(unsigned long long top, const xf& Ta, const xf& Tb, const TreeCtx& C, const HitOut& H, long long base,
+                                             int& count, unsigned long long* stack, int& sp, int* __restrict__ overflowFlag) {
+  const int lane = threadIdx.x & 31;
+  int n1 = (int)(top >> 32), n2 = (int)(top & 0xffffffffu);
+  bool l1 = C.ndFirst[n1] < 0, l2 = C.ndFirst[n2] < 0;
+  double r1p = C.ndR[n1], r2p = C.ndR[n2];
+  bool descend2;  // iterate the children of node2?
+  if (l1) descend2 = true; else if (l2) descend2 = false; else descend2 = (r1p <= r2p);
+  int dn = descend2 ? n2 : n1;
+  int first = C.ndFirst[dn], cnt = C.ndCount[dn];
+  for (int k0 = 0; k0 < cnt; k0 += 32) {
+    int k = k0 + lane;
+    bool push = false, emit = false;
+    int m1 = n1, m2 = n2;
+    d3 c1, c2;
+    double r1 = 0, r2 = 0, dist = 0;
+    if (k < cnt) {
+      if (descend2) m2 = first + k; else m1 = first + k;
+      c1 = xfP(Ta, ld3(C.ndC + 3 * m1));
+      c2 = xfP(Tb, ld3(C.ndC + 3 * m2));
+      r1 = C.ndR[m1];
+      r2 = C.ndR[m2];
+      if (vdist2(c1, c2) < (r1 + r2) * (r1 + r2)) {
+        if (C.ndFirst[m1] < 0 && C.ndFirst[m2] < 0) {
+          dist = vdist(c1, c2);
+          emit = dist < r2 + r1;
+        } else {
+          push = true;
+        }
+      }
+    }
+    unsigned pm = __ballot_sync(0xffffffffu, push), em = __ballot_sync(0xffffffffu, emit);
+    if (push) {
+      int pos = sp + __popc(pm & ((1u << lane) - 1));
+      if (pos < TREE_STACK) stack[pos] = ((unsigned long long)(unsigned)m1 << 32) | (unsigned)m2;
+    }
+    sp += __popc(pm);
+    if (sp > TREE_STACK) { if (lane == 0) *overflowFlag = 1; sp = TREE_STACK; }
+    if (emit && EMIT) {
+      int pos = count + __popc(em & ((1u << lane) - 1));
+      double dbc = r2 + r1;
+      double alpha = (r1 - r2 + dist) / (2 * dist);
+      d3 p((1 - alpha) * c1.x + alpha * c2.x, (1 - alpha) * c1.y + alpha * c2.y, (1 - alpha) * c1.z + alpha * c2.z);
+      d3 nrm = vnormalize(vsub(c2, c1));
+      writeHit(H, base + pos, p, nrm, dist - dbc, 0, m1, m2, -1);
+    }
+    count += __popc(em);
+    __syncwarp();
+  }
+}
+
 template <bool EMIT>
 __device__ __forceinline__ void narrowTreePair(int i, unsigned long long* stack, const unsigned long long* __restrict__ pairVal,
                                                const int* __restrict__ pairType, const int* __restrict__ pairSlot,
                                                const TreeCtx& C, const HitOut& H, int* __restrict__ pairCountOrCap,
-                                               int* __restrict__ overflowFlag) {
+                                               int* __restrict__ overflowFlag, const TreeTasks& T) {
   int lane = threadIdx.x & 31;
   int pt = pairType[i];
   int a = (int)(pairVal[i] >> 32), b = (int)(pairVal[i] & 0xffffffffu);
@@ -364,56 +433,28 @@ __device__ __forceinline__ void narrowTreePair(int i, unsigned long long* stack,
       }
     }
     __syncwarp();
-    while (sp > 0) {
-      unsigned long long top = stack[sp - 1];
-      sp--;
+    // Breadth first while the frontier is small: a pair of meshes pressed together holds 10^3 - 10^4 leaf x leaf contacts,
+    // and one warp walking all of it was the tail of the whole narrowphase.  Once SPLIT_TARGET node pairs are waiting, they
+    // are handed to the task list (one warp each, k_tree_tasks) and this warp is done; small pairs finish right here.  The
+    // contacts of a pair are emitted in the order [this prefix][task 0][task 1]... - the same in the count and in the emit
+    // pass, which walk identically.
+    int head = 0;
+    while (head < sp && sp - head < T.target && sp <= TREE_STACK - 64) {
+      unsigned long long top = stack[head];
+      head++;
       __syncwarp();
-      int n1 = (int)(top >> 32), n2 = (int)(top & 0xffffffffu);
-      bool l1 = C.ndFirst[n1] < 0, l2 = C.ndFirst[n2] < 0;
-      double r1p = C.ndR[n1], r2p = C.ndR[n2];
-      bool descend2;  // iterate the children of node2?
-      if (l1) descend2 = true; else if (l2) descend2 = false; else descend2 = (r1p <= r2p);
-      int dn = descend2 ? n2 : n1;
-      int first = C.ndFirst[dn], cnt = C.ndCount[dn];
-      for (int k0 = 0; k0 < cnt; k0 += 32) {
-        int k = k0 + lane;
-        bool push = false, emit = false;
-        int m1 = n1, m2 = n2;
-        d3 c1, c2;
-        double r1 = 0, r2 = 0, dist = 0;
-        if (k < cnt) {
-          if (descend2) m2 = first + k; else m1 = first + k;
-          c1 = xfP(Ta, ld3(C.ndC + 3 * m1));
-          c2 = xfP(Tb, ld3(C.ndC + 3 * m2));
-          r1 = C.ndR[m1];
-          r2 = C.ndR[m2];
-          if (vdist2(c1, c2) < (r1 + r2) * (r1 + r2)) {
-            if (C.ndFirst[m1] < 0 && C.ndFirst[m2] < 0) {
-              dist = vdist(c1, c2);
-              emit = dist < r2 + r1;
-            } else {
-              push = true;
-            }
-          }
-        }
-        unsigned pm = __ballot_sync(0xffffffffu, push), em = __ballot_sync(0xffffffffu, emit);
-        if (push) {
-          int pos = sp + __popc(pm & ((1u << lane) - 1));
-          if (pos < TREE_STACK) stack[pos] = ((unsigned long long)(unsigned)m1 << 32) | (unsigned)m2;
-        }
-        sp += __popc(pm);
-        if (sp > TREE_STACK) { if (lane == 0) *overflowFlag = 1; sp = TREE_STACK; }
-        if (emit && EMIT) {
-          int pos = count + __popc(em & ((1u << lane) - 1));
-          double dbc = r2 + r1;
-          double alpha = (r1 - r2 + dist) / (2 * dist);
-          d3 p((1 - alpha) * c1.x + alpha * c2.x, (1 - alpha) * c1.y + alpha * c2.y, (1 - alpha) * c1.z + alpha * c2.z);
-          d3 nrm = vnormalize(vsub(c2, c1));
-          writeHit(H, base + pos, p, nrm, dist - dbc, 0, m1, m2, -1);
-        }
-        count += __popc(em);
-        __syncwarp();
+      treeTreeStep<EMIT>(top, Ta, Tb, C, H, base, count, stack, sp, overflowFlag);
+    }
+    int nT = sp - head;
+    if (!EMIT) {
+      int start = 0;
+      if (nT > 0) {
+        if (lane == 0) start = atomicAdd(T.counter, nT);
+        start = __shfl_sync(0xffffffffu, start, 0);
+        if (start + nT <= T.cap)
+          for (int j = lane; j < nT; j += 32) { T.val[start + j] = stack[head + j]; T.pair[start + j] = i; }
       }
+      if (lane == 0) { T.pairStart[i] = start; T.pairN[i] = nT; }
     }
   } else {
     // single tree against a plane or a box: stack of node indices
@@ -484,7 +525,16 @@ __device__ __forceinline__ void narrowTreePair(int i, unsigned long long* stack,
       }
     }
   }
-  if (lane == 0) pairCountOrCap[i] = count;
+  if (!EMIT) {
+    if (lane == 0) {
+      T.pairPrefix[i] = count;        // (k_tree_paircap adds the tasks' contacts to pairCap)
+      pairCountOrCap[i] = count;
+      if (pt != PT_TREETREE) T.pairN[i] = 0;
+    }
+  } else if (lane == 0) {
+    int s0 = T.pairStart[i], n = T.pairN[i];
+    pairCountOrCap[i] = count + (n > 0 ? T.prefix[s0 + n] - T.prefix[s0] : 0);
+  }
 }
 
 // One warp per entry of the tree-pair list written by k_pair_classify (scenes of boxes with a few meshes have a
@@ -494,14 +544,51 @@ template <bool EMIT>
 __global__ void k_narrow_tree(const int* __restrict__ treeList, const int* __restrict__ treeCount,
                               const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairType,
                               const int* __restrict__ pairSlot, TreeCtx C, HitOut H, int* __restrict__ pairCountOrCap,
-                              int* __restrict__ overflowFlag) {
+                              int* __restrict__ overflowFlag, TreeTasks T) {
   __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TREE_STACK];
   int warp = threadIdx.x >> 5;
   int n = *treeCount;
   for (int t = blockIdx.x * WARPS_PER_BLOCK + warp; t < n; t += gridDim.x * WARPS_PER_BLOCK) {
-    narrowTreePair<EMIT>(treeList[t], stackMem[warp], pairVal, pairType, pairSlot, C, H, pairCountOrCap, overflowFlag);
+    narrowTreePair<EMIT>(treeList[t], stackMem[warp], pairVal, pairType, pairSlot, C, H, pairCountOrCap, overflowFlag, T);
     __syncwarp();
   }
+}
+
+// One warp per task: the depth-first descent from one node pair of a tree x tree candidate pair.
+template <bool EMIT>
+__global__ void k_tree_tasks(int nTasks, const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairSlot, TreeCtx C, HitOut H,
+                             int* __restrict__ overflowFlag, TreeTasks T) {
+  __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TREE_STACK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned long long* stack = stackMem[warp];
+  for (int t = blockIdx.x * WARPS_PER_BLOCK + warp; t < nTasks; t += gridDim.x * WARPS_PER_BLOCK) {
+    const int i = T.pair[t];
+    const int a = (int)(pairVal[i] >> 32), b = (int)(pairVal[i] & 0xffffffffu);
+    xf Ta, Tb;
+    Ta.R = ldm(C.shR + 9 * a); Ta.t = ld3(C.shX + 3 * a);
+    Tb.R = ldm(C.shR + 9 * b); Tb.t = ld3(C.shX + 3 * b);
+    long long base = 0;
+    if (EMIT) base = (long long)pairSlot[i] + T.pairPrefix[i] + (T.prefix[t] - T.prefix[T.pairStart[i]]);
+    int count = 0, sp = 1;
+    if (lane == 0) stack[0] = T.val[t];
+    __syncwarp();
+    while (sp > 0) {
+      unsigned long long top = stack[sp - 1];
+      sp--;
+      __syncwarp();
+      treeTreeStep<EMIT>(top, Ta, Tb, C, H, base, count, stack, sp, overflowFlag);
+    }
+    if (!EMIT && lane == 0) T.count[t] = count;
+    __syncwarp();
+  }
+}
+// capacity of a tree pair = the contacts of its prefix walk + those of its tasks
+__global__ void k_tree_paircap(const int* __restrict__ treeList, const int* __restrict__ treeCount, TreeTasks T, int* __restrict__ pairCap) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *treeCount) return;
+  int i = treeList[t];
+  int n = T.pairN[i];
+  if (n > 0) pairCap[i] = T.pairPrefix[i] + (T.prefix[T.pairStart[i] + n] - T.prefix[T.pairStart[i]]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -56,9 +56,35 @@ static void detect(am3d_ctx* c) {
     bool haveTrees = c->NN > 0;
     CK(cudaMemsetAsync(c->counters.p + 1, 0, sizeof(int), c->stream));
     CK(cudaEventRecord(c->ev[16], c->stream));
-    if (haveTrees)
-      LAUNCH(c, k_narrow_tree<false>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
-             c->pairSlot.p, TC, HO, c->pairCap.p, c->counters.p + 1);
+    // sphere-tree pairs: count pass.  A tree x tree pair whose frontier grows past SPLIT_TARGET node pairs hands them to
+    // the task list (one warp per node pair, k_tree_tasks); the pair's contacts are then [its own prefix walk][task 0][task 1]...
+    TreeTasks TT{};
+    int nTasks = 0;
+    if (haveTrees) {
+      c->treePairStart.ensure(np + 1); c->treePairN.ensure(np + 1); c->treePairPrefix.ensure(np + 1);
+      if (c->taskVal.cap == 0) { c->taskVal.ensure(65536); c->taskPair.ensure(65536); }
+      for (int attempt = 0; attempt < 3; attempt++) {
+        CK(cudaMemsetAsync(c->counters.p + 10, 0, sizeof(int), c->stream));
+        TT = TreeTasks{c->taskVal.p, c->taskPair.p, nullptr, nullptr, c->counters.p + 10, (int)std::min<size_t>(c->taskVal.cap, 0x7fffffff), c->treeSplit ? SPLIT_TARGET : 0x7fffffff,
+                       c->treePairStart.p, c->treePairN.p, c->treePairPrefix.p};
+        LAUNCH(c, k_narrow_tree<false>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
+               c->pairSlot.p, TC, HO, c->pairCap.p, c->counters.p + 1, TT);
+        nTasks = readInt(c, c->counters.p + 10);
+        if ((size_t)nTasks <= c->taskVal.cap) break;
+        size_t cap = (size_t)nTasks + nTasks / 4 + 1024;
+        c->taskVal.ensure(cap); c->taskPair.ensure(cap);
+      }
+      if (nTasks > 0) {
+        c->taskCount.ensure(nTasks + 2); c->taskPrefix.ensure(nTasks + 2);
+        TT.count = c->taskCount.p;
+        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 16);
+        LAUNCH(c, k_tree_tasks<false>, taskGrid, WARPS_PER_BLOCK * 32, nTasks, c->pairValSorted.p, c->pairSlot.p, TC, HO, c->counters.p + 1, TT);
+        CK(cudaMemsetAsync(c->taskCount.p + nTasks, 0, sizeof(int), c->stream));
+        cubRun(c, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, c->taskCount.p, c->taskPrefix.p, nTasks + 1, c->stream); });
+        TT.prefix = c->taskPrefix.p;
+        LAUNCH(c, k_tree_paircap, nblk(np), BLK, c->treeList.p, c->counters.p + 7, TT, c->pairCap.p);
+      }
+    }
     CK(cudaEventRecord(c->ev[17], c->stream));
     int nslots = scanTotal(c, c->pairCap, c->pairSlot, np);
     c->nSlots = nslots;
@@ -69,9 +95,14 @@ static void detect(am3d_ctx* c) {
     CK(cudaEventRecord(c->ev[18], c->stream));
     LAUNCH(c, k_narrow_box, nblk(np, 128), 128, np, c->pairValSorted.p, c->pairType.p, c->pairSlot.p, c->shSize.p, c->shRadius.p,
            c->shX.p, c->shR.p, HO, c->pairCount.p);
-    if (haveTrees)
+    if (haveTrees) {
       LAUNCH(c, k_narrow_tree<true>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
-             c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1);
+             c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1, TT);
+      if (nTasks > 0) {
+        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 16);
+        LAUNCH(c, k_tree_tasks<true>, taskGrid, WARPS_PER_BLOCK * 32, nTasks, c->pairValSorted.p, c->pairSlot.p, TC, HO, c->counters.p + 1, TT);
+      }
+    }
     CK(cudaEventRecord(c->ev[19], c->stream));
     c->narrowTimed = true;
     nc = scanTotal(c, c->pairCount, c->pairOut, np);

@@ -349,12 +349,21 @@ __device__ __forceinline__ int warmLookup(const WarmCtx& W, int lo, int hi, unsi
   }
   int nt = W.np - W.npSorted;
   if (nt > 0) {  // entries appended later in the list (by an unmerge) win over earlier duplicates
+    // (among themselves the duplicates of a box x tree pair again follow the reference's emission order: the contacts
+    // of an unmerged pair return in their BodyPairContact.contactList order, i.e. by node rank - not in the order this
+    // library happened to store them at the merge)
     int tl = 0, th = nt;
     while (tl < th) { int mid = (tl + th) >> 1; if (W.tailKey[mid] < k0) tl = mid + 1; else th = mid; }
+    int tbest = -1, tRank = -1;
     for (int t = tl; t < nt && W.tailKey[t] == k0; t++) {
       int j = W.tailIdx[t];
-      if (W.pkey1[j] == k1) { best = j; bestRank = 0x7fffffff; }
+      if (W.pkey1[j] == k1) {
+        int lf = W.pleaf[j];
+        int rk = lf >= 0 ? W.ndRank[lf] : 0;
+        if (tbest < 0 || rk >= tRank) { tbest = j; tRank = rk; }
+      }
     }
+    if (tbest >= 0) best = tbest;
   }
   return best;
 }
