@@ -323,7 +323,7 @@ struct TreeCtx {
   const int* ndCount;
 };
 
-#define SPLIT_TARGET 64  // node pairs waiting at which a tree x tree pair is handed over to one warp per node pair
+#define SPLIT_TARGET 512  // node pairs waiting at which a tree x tree pair is handed over to one warp per node pair
 struct TreeTasks {
   unsigned long long* val;  // node pair (node of tree 1 << 32 | node of tree 2) a task starts from
   int* pair;                // candidate pair it belongs to
@@ -342,7 +342,8 @@ struct TreeTasks {
 // pairs that are not leaf x leaf are pushed at stack[sp..], leaf x leaf contacts are counted (EMIT: written at base + count).
 template <bool EMIT>
 __device__ __forceinline__ void treeTreeStep(unsigned long long top, const xf& Ta, const xf& Tb, const TreeCtx& C, const HitOut& H, long long base,
-                                             int& count, unsigned long long* stack, int& sp, int* __restrict__ overflowFlag) {
+                                             int& count, unsigned long long* stack, int& sp, int* __restrict__ overflowFlag,
+                                             const int stackCap = TREE_STACK) {
   const int lane = threadIdx.x & 31;
   int n1 = (int)(top >> 32), n2 = (int)(top & 0xffffffffu);
   bool l1 = C.ndFirst[n1] < 0, l2 = C.ndFirst[n2] < 0;
@@ -375,10 +376,10 @@ __device__ __forceinline__ void treeTreeStep(unsigned long long top, const xf& T
     unsigned pm = __ballot_sync(0xffffffffu, push), em = __ballot_sync(0xffffffffu, emit);
     if (push) {
       int pos = sp + __popc(pm & ((1u << lane) - 1));
-      if (pos < TREE_STACK) stack[pos] = ((unsigned long long)(unsigned)m1 << 32) | (unsigned)m2;
+      if (pos < stackCap) stack[pos] = ((unsigned long long)(unsigned)m1 << 32) | (unsigned)m2;
     }
     sp += __popc(pm);
-    if (sp > TREE_STACK) { if (lane == 0) *overflowFlag = 1; sp = TREE_STACK; }
+    if (sp > stackCap) { if (lane == 0) *overflowFlag = 1; sp = stackCap; }
     if (emit && EMIT) {
       int pos = count + __popc(em & ((1u << lane) - 1));
       double dbc = r2 + r1;
@@ -554,11 +555,14 @@ __global__ void k_narrow_tree(const int* __restrict__ treeList, const int* __res
   }
 }
 
-// One warp per task: the depth-first descent from one node pair of a tree x tree candidate pair.
+// One warp per task: the depth-first descent from one node pair of a tree x tree candidate pair.  A depth-first stack
+// holds at most (levels of both trees) x (fan-out) entries - a small one keeps the shared memory per warp at 4 KB and the
+// occupancy at what the registers allow (the walk is a chain of dependent loads: it lives on resident warps).
+#define TASK_STACK 512
 template <bool EMIT>
 __global__ void k_tree_tasks(int nTasks, const unsigned long long* __restrict__ pairVal, const int* __restrict__ pairSlot, TreeCtx C, HitOut H,
                              int* __restrict__ overflowFlag, TreeTasks T) {
-  __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TREE_STACK];
+  __shared__ unsigned long long stackMem[WARPS_PER_BLOCK][TASK_STACK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned long long* stack = stackMem[warp];
   for (int t = blockIdx.x * WARPS_PER_BLOCK + warp; t < nTasks; t += gridDim.x * WARPS_PER_BLOCK) {
@@ -576,7 +580,7 @@ __global__ void k_tree_tasks(int nTasks, const unsigned long long* __restrict__ 
       unsigned long long top = stack[sp - 1];
       sp--;
       __syncwarp();
-      treeTreeStep<EMIT>(top, Ta, Tb, C, H, base, count, stack, sp, overflowFlag);
+      treeTreeStep<EMIT>(top, Ta, Tb, C, H, base, count, stack, sp, overflowFlag, TASK_STACK);
     }
     if (!EMIT && lane == 0) T.count[t] = count;
     __syncwarp();

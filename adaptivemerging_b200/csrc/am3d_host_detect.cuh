@@ -77,7 +77,7 @@ static void detect(am3d_ctx* c) {
       if (nTasks > 0) {
         c->taskCount.ensure(nTasks + 2); c->taskPrefix.ensure(nTasks + 2);
         TT.count = c->taskCount.p;
-        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 16);
+        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 32);
         LAUNCH(c, k_tree_tasks<false>, taskGrid, WARPS_PER_BLOCK * 32, nTasks, c->pairValSorted.p, c->pairSlot.p, TC, HO, c->counters.p + 1, TT);
         CK(cudaMemsetAsync(c->taskCount.p + nTasks, 0, sizeof(int), c->stream));
         cubRun(c, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, c->taskCount.p, c->taskPrefix.p, nTasks + 1, c->stream); });
@@ -99,7 +99,7 @@ static void detect(am3d_ctx* c) {
       LAUNCH(c, k_narrow_tree<true>, treeGrid, WARPS_PER_BLOCK * 32, c->treeList.p, c->counters.p + 7, c->pairValSorted.p, c->pairType.p,
              c->pairSlot.p, TC, HO, c->pairCount.p, c->counters.p + 1, TT);
       if (nTasks > 0) {
-        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 16);
+        int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 32);
         LAUNCH(c, k_tree_tasks<true>, taskGrid, WARPS_PER_BLOCK * 32, nTasks, c->pairValSorted.p, c->pairSlot.p, TC, HO, c->counters.p + 1, TT);
       }
     }
