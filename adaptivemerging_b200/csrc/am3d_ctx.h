@@ -245,6 +245,8 @@ struct am3d_ctx {
   int useClusters = 1, maxClusters = 0, nPart = 0, hPartScenes = 0;
   DevBuf<int> partRange, partSceneStart, partRemaining;
   std::vector<int> hPartSceneStart, hPartCount;
+  int useTailFusion = 1;  // am3d_set_option("pgs_tail_fusion", 0/1): trailing phases with one group per scene in one launch (k_pgs_tail)
+  DevBuf<int> tailTable;
   int treeSplit = 1;      // am3d_set_option("tree_split", 0/1): tree x tree pairs with a large frontier are split into one task per node pair
   int fastRows = 1;       // am3d_set_option("pgs_fast_rows", 0/1): branch-free PGS row update (bit-identical results; 0 = the plain form everywhere)
   int useGiantWarps = 1;  // am3d_set_option("giant_warps", 0/1): groups of >= 65 contacts are solved by a warp (k_pgs_giant)  // (layer, colour) phases of the sorted group list

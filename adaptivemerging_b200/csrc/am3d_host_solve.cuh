@@ -320,27 +320,47 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
       CK(cudaGetLastError());
       c->kernelLaunches++;
     };
-    for (int k = 0; k < c->nColors; k++) {
-      int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-      if (giants[k] > 0) { giantLaunch(0, g0, giants[k], 0); g0 += giants[k]; }
-      if (hubs) LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
-      else LAUNCH(c, (k_pgs_color<0, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
-      int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
-      if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 0, 0);
+    // tail phases with at most one group per scene (batched scenes): one launch for all of them, a thread per scene
+    int cTail = c->nColors;
+    if (c->useTailFusion && !hubs && nScenes >= 8) {
+      while (cTail > 0 && giants[cTail - 1] == 0 && c->colorStart[cTail] - c->colorStart[cTail - 1] <= nScenes) cTail--;
+      if (c->nColors - cTail < 2) cTail = c->nColors;
     }
-    for (int it = 0; it < iterations; it++) {
-      int last = it == iterations - 1;
-      for (int k = 0; k < c->nColors; k++) {
+    const int nTail = c->nColors - cTail;
+    if (nTail > 0) {
+      c->tailTable.ensure((size_t)nTail * nScenes + 1);
+      CK(cudaMemsetAsync(c->tailTable.p, 0xff, ((size_t)nTail * nScenes + 1) * sizeof(int), c->stream));
+      int gT = c->colorStart[cTail];
+      LAUNCH(c, k_tail_table, nblk(ng - gT), BLK, gT, ng, cTail, nScenes, c->sgPhase.p, S.sgScene, c->tailTable.p, c->tailTable.p + (size_t)nTail * nScenes);
+      int dup = readInt(c, c->tailTable.p + (size_t)nTail * nScenes);
+      if (dup != -1) cTail = c->nColors;  // (the flag word starts as -1 like the table)
+    }
+    const int nTailUse = c->nColors - cTail;
+    auto phaseLaunches = [&](int mode, int last) {
+      for (int k = 0; k < cTail; k++) {
         int g0 = c->colorStart[k], g1 = c->colorStart[k + 1];
-        if (giants[k] > 0) { giantLaunch(1, g0, giants[k], last); g0 += giants[k]; }
-        if (hubs) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
-        else LAUNCH(c, (k_pgs_color<1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        if (giants[k] > 0) { giantLaunch(mode, g0, giants[k], last); g0 += giants[k]; }
+        if (mode == 0) {
+          if (hubs) LAUNCH(c, (k_pgs_color<0, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+          else LAUNCH(c, (k_pgs_color<0, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, 0, c->iterState.p);
+        } else {
+          if (hubs) LAUNCH(c, (k_pgs_color<1, true>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+          else LAUNCH(c, (k_pgs_color<1, false>), nblk(g1 - g0, 128), 128, g0, g1, S, c->dv.p, PP, last, c->iterState.p);
+        }
         int r0 = c->colorRunStart[k], r1 = c->colorRunStart[k + 1];
-        if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, 1, PP.check);
-        if (!sweep) c->solveLaunches++;
+        if (r1 > r0) LAUNCH(c, k_hub_reduce, nblk((long long)(r1 - r0) * 32, 128), 128, r0, r1, HR, S, c->dv.p, c->iterState.p, mode, mode ? PP.check : 0);
+        if (mode == 1 && !sweep) c->solveLaunches++;
       }
-      LAUNCH(c, k_iter_end, nblk(nScenes), BLK, S, PP, c->iterState.p);
-    }
+      if (nTailUse > 0) {
+        if (mode == 0) LAUNCH(c, k_pgs_tail<0>, nblk(nScenes, 128), 128, nTailUse, c->tailTable.p, S, c->dv.p, PP, 0, c->iterState.p, 0);
+        else LAUNCH(c, k_pgs_tail<1>, nblk(nScenes, 128), 128, nTailUse, c->tailTable.p, S, c->dv.p, PP, last, c->iterState.p, 1);
+        if (mode == 1 && !sweep) c->solveLaunches++;
+      } else if (mode == 1) {
+        LAUNCH(c, k_iter_end, nblk(nScenes), BLK, S, PP, c->iterState.p);
+      }
+    };
+    phaseLaunches(0, 0);
+    for (int it = 0; it < iterations; it++) phaseLaunches(1, it == iterations - 1);
   }
   CK(cudaEventRecord(c->ev[sweep ? 9 : 11], c->stream));
   if (!sweep) CK(cudaMemsetAsync(c->bp.nActive.p, 0, (nExt + 1) * sizeof(int), c->stream));

@@ -1659,6 +1659,33 @@ k_pgs_color(int gBegin, int gEnd, SolveArrays S, double* __restrict__ dv, PgsPar
   if (p < gEnd) pgsGroup<MODE, HUB>(p, S, dv, P, lastIter);
 }
 
+// Tail phases of batched scenes.  A body touched by many pairs (the platform of tower25platform.xml: 13) forces as many
+// colours, and the last of them hold nothing but ITS pairs: one group per scene.  A launch per such phase is pure latency
+// (32 CTAs on 148 SMs, two dependent loads and one short chain each).  They are folded into ONE launch with a thread per
+// scene that walks its scene's groups of those phases in phase order - the same Gauss-Seidel sequence, since a scene's
+// groups never meet another scene's - and, in the full solve, closes the iteration for its scene (sceneIterEnd) right
+// away.  table[(phase - c0) * nScenes + scene] = the scene's group in that phase or -1 (k_tail_table).
+__global__ void k_tail_table(int g0, int ng, int c0, int nScenes, const int* __restrict__ sgPhase, const int* __restrict__ sgScene,
+                             int* __restrict__ table, int* __restrict__ dupFlag) {
+  int p = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ng) return;
+  int old = atomicExch(table + (size_t)(sgPhase[p] - c0) * nScenes + sgScene[p], p);
+  if (old != -1) *dupFlag = 1;  // two groups of one scene in a tail phase: the caller takes the launch-per-phase path
+}
+template <int MODE>
+__global__ void __launch_bounds__(128)
+k_pgs_tail(int nTail, const int* __restrict__ table, SolveArrays S, double* __restrict__ dv, PgsParams P, int lastIter,
+           unsigned long long* __restrict__ iterState, int closeIteration) {
+  if (MODE == 1 && iterState[1]) return;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= P.nScenes) return;
+  for (int k = 0; k < nTail; k++) {
+    int p = table[(size_t)k * P.nScenes + s];
+    if (p >= 0) pgsGroup<MODE, false>(p, S, dv, P, lastIter);
+  }
+  if (MODE == 1 && closeIteration) sceneIterEnd(s, P, S.sceneState, iterState);
+}
+
 // The whole solve in ONE cooperative launch: warm-start pass, then `iterations` sweeps, one grid-wide barrier per
 // colour (two when the colour has hub runs).  Used when the colours are many and small (batched scenes): thousands
 // of tiny launches become grid barriers.  Same Gauss-Seidel sequence as the per-colour launches.
