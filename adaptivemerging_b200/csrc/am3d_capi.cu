@@ -1,6 +1,7 @@
 // C ABI (include/am3d.h) and the per-step kernel sequence.
 // Sequence = RigidBodySystem.advanceTime (RigidBodySystem.java:102-185); see stepOnce().
 #include "am3d_host_util.cuh"
+#include "am3d_sort.cuh"
 #include "am3d_host_scene.cuh"
 #include "am3d_host_detect.cuh"
 #include "am3d_host_solve.cuh"
@@ -120,9 +121,7 @@ static void sortBpPrev(am3d_ctx* c) {
   if (n < 2) return;
   c->tmpI0.ensure(n + 2); c->tmpI1.ensure(n + 2); c->grpKey.ensure(n + 2); c->grpKeySorted.ensure(n + 2);
   LAUNCH(c, k_iota, nblk(n), BLK, n, c->tmpI0.p);
-  cubRun(c, [&](void* t, size_t& b) {
-    return cub::DeviceRadixSort::SortPairs(t, b, c->bpPrev.key.p, c->grpKeySorted.p, c->tmpI0.p, c->tmpI1.p, n, 0, 48, c->stream);
-  });
+  sortPairs(c, c->bpPrev.key.p, c->grpKeySorted.p, c->tmpI0.p, c->tmpI1.p, n, 0, 48);
   c->bpTmp.ensure(n + 1);
   LAUNCH(c, k_bpc_gather, nblk(n), BLK, n, c->tmpI1.p, c->bpPrev.key.p, c->bpPrev.b1.p, c->bpPrev.b2.p, c->bpPrev.metricHist.p,
          c->bpPrev.stateHist.p, c->bpPrev.nMetric.p, c->bpPrev.nState.p, c->bpTmp.key.p, c->bpTmp.b1.p, c->bpTmp.b2.p,
@@ -926,6 +925,7 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   else if (!strcmp(name, "giant_warps")) c->useGiantWarps = (int)value;
   else if (!strcmp(name, "pgs_fast_rows")) c->fastRows = value != 0;
   else if (!strcmp(name, "tree_split")) c->treeSplit = value != 0;
+  else if (!strcmp(name, "own_primitives")) c->ownPrimitives = value != 0;
   else if (!strcmp(name, "pgs_tail_fusion")) c->useTailFusion = value != 0;
   else if (!strcmp(name, "pgs_clusters")) c->useClusters = (int)value;
   else if (!strcmp(name, "giant_chunk")) c->giantChunk = (int)value;

@@ -245,6 +245,9 @@ struct am3d_ctx {
   int useClusters = 1, maxClusters = 0, nPart = 0, hPartScenes = 0;
   DevBuf<int> partRange, partSceneStart, partRemaining;
   std::vector<int> hPartSceneStart, hPartCount;
+  int ownPrimitives = 1;  // am3d_set_option("own_primitives", 0/1): hand-written radix sort / prefix sum (am3d_sort.cuh) or the CUB ones
+  DevBuf<unsigned long long> rsKeyTmp, rsValTmp;
+  DevBuf<int> rsHist, rsOff, scanSums;
   int useTailFusion = 1;  // am3d_set_option("pgs_tail_fusion", 0/1): trailing phases with one group per scene in one launch (k_pgs_tail)
   DevBuf<int> tailTable;
   int treeSplit = 1;      // am3d_set_option("tree_split", 0/1): tree x tree pairs with a large frontier are split into one task per node pair

@@ -1,6 +1,7 @@
 // Host orchestration of detection, body-pair bookkeeping and warm start.
 #pragma once
 #include "am3d_host_util.cuh"
+#include "am3d_sort.cuh"
 #include "am3d_detect.cuh"
 #include "am3d_step.cuh"
 static void detect(am3d_ctx* c) {
@@ -17,9 +18,7 @@ static void detect(am3d_ctx* c) {
     LAUNCH(c, k_cell_keys, nblk(c->nSmall), BLK, c->nSmall, c->smallList.p, c->shBody.p, c->scene.p, c->shBoundC.p, inv,
            c->cellKey.p, c->cellVal.p);
     int endBit = std::min(64, 42 + bitsFor((unsigned long long)c->H.nscenes));
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->cellKey.p, c->cellKeySorted.p, c->cellVal.p, c->cellValSorted.p, c->nSmall, 0, endBit, c->stream);
-    });
+    sortPairs(c, c->cellKey.p, c->cellKeySorted.p, c->cellVal.p, c->cellValSorted.p, c->nSmall, 0, endBit);
   }
   int np = 0;
   for (int attempt = 0; attempt < 3; attempt++) {
@@ -42,9 +41,7 @@ static void detect(am3d_ctx* c) {
   int nc = 0;
   if (np > 0) {
     int endBit = 2 * bitsFor((unsigned long long)c->NB) + (c->haveComposites ? 16 : 0);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->pairKey.p, c->pairKeySorted.p, c->pairVal.p, c->pairValSorted.p, np, 0, endBit, c->stream);
-    });
+    sortPairs(c, c->pairKey.p, c->pairKeySorted.p, c->pairVal.p, c->pairValSorted.p, np, 0, endBit);
     c->pairType.ensure(np + 1); c->pairCap.ensure(np + 1); c->pairSlot.ensure(np + 1); c->pairCount.ensure(np + 1); c->pairOut.ensure(np + 1);
     c->treeList.ensure(np + 1);
     CK(cudaMemsetAsync(c->counters.p + 7, 0, sizeof(int), c->stream));
@@ -80,7 +77,7 @@ static void detect(am3d_ctx* c) {
         int taskGrid = std::min(nblk(nTasks, WARPS_PER_BLOCK), 148 * 32);
         LAUNCH(c, k_tree_tasks<false>, taskGrid, WARPS_PER_BLOCK * 32, nTasks, c->pairValSorted.p, c->pairSlot.p, TC, HO, c->counters.p + 1, TT);
         CK(cudaMemsetAsync(c->taskCount.p + nTasks, 0, sizeof(int), c->stream));
-        cubRun(c, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, c->taskCount.p, c->taskPrefix.p, nTasks + 1, c->stream); });
+        exclusiveSum(c, c->taskCount.p, c->taskPrefix.p, nTasks + 1);
         TT.prefix = c->taskPrefix.p;
         LAUNCH(c, k_tree_paircap, nblk(np), BLK, c->treeList.p, c->counters.p + 7, TT, c->pairCap.p);
       }
@@ -154,9 +151,7 @@ static void warmStart(am3d_ctx* c, bool postStab = false) {
   if (nt > 0) {  // index the out-of-order tail of last step's contact list (appended by an unmerge)
     c->tailKey.ensure(nt + 1); c->tailKeySorted.ensure(nt + 1); c->tailVal.ensure(nt + 1); c->tailIdx.ensure(nt + 1);
     LAUNCH(c, k_tail_keys, nblk(nt), BLK, nt, c->prev.nSorted, c->prev.key0.p, c->tailKey.p, c->tailVal.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->tailKey.p, c->tailKeySorted.p, c->tailVal.p, c->tailIdx.p, nt, 0, 64, c->stream);
-    });
+    sortPairs(c, c->tailKey.p, c->tailKeySorted.p, c->tailVal.p, c->tailIdx.p, nt, 0, 64);
   }
   c->wsPairSlow.ensure(nbp + 1); c->wsMatch.ensure(c->cur.n + 1);
   CK(cudaMemsetAsync(c->wsPairSlow.p, 0, nbp * sizeof(int), c->stream));
@@ -167,13 +162,9 @@ static void warmStart(am3d_ctx* c, bool postStab = false) {
     c->wsKa.ensure(ns + 1); c->wsKb.ensure(ns + 1); c->wsK0s.ensure(ns + 1); c->wsK1s.ensure(ns + 1);
     c->wsIa.ensure(ns + 1); c->wsIb.ensure(ns + 1); c->wsIdx.ensure(ns + 1);
     LAUNCH(c, k_iota, nblk(ns), BLK, ns, c->wsIa.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->prev.key1.p, c->wsKa.p, c->wsIa.p, c->wsIb.p, ns, 0, 64, c->stream);
-    });
+    sortPairs(c, c->prev.key1.p, c->wsKa.p, c->wsIa.p, c->wsIb.p, ns, 0, 64);
     LAUNCH(c, k_gather_u64, nblk(ns), BLK, ns, c->wsIb.p, c->prev.key0.p, c->wsKb.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->wsKb.p, c->wsK0s.p, c->wsIb.p, c->wsIdx.p, ns, 0, 64, c->stream);
-    });
+    sortPairs(c, c->wsKb.p, c->wsK0s.p, c->wsIb.p, c->wsIdx.p, ns, 0, 64);
     LAUNCH(c, k_gather_u64, nblk(ns), BLK, ns, c->wsIdx.p, c->prev.key1.p, c->wsK1s.p);
   }
   WarmCtx W{c->cur.b1.p, c->cur.b2.p, c->cur.s1.p, c->cur.s2.p, c->cur.leaf.p, c->cur.key0.p, c->cur.key1.p, c->cur.pB1.p,

@@ -1,6 +1,7 @@
 // Scene upload and reset: RigidBodySystem.reset() (RigidBodySystem.java:390-426) on the device arrays.
 #pragma once
 #include "am3d_host_util.cuh"
+#include "am3d_sort.cuh"
 #include "am3d_step.cuh"
 // ------------------------------------------------------------------------------------------------
 static void copyScene(am3d_ctx* c, const am3d_scene* s) {

@@ -1,6 +1,7 @@
 // Host orchestration of the two PGS solves (full solve and single sweep) and of merge / unmerge.
 #pragma once
 #include "am3d_host_util.cuh"
+#include "am3d_sort.cuh"
 #include "am3d_merge.cuh"
 #include "am3d_step.cuh"
 
@@ -63,9 +64,7 @@ static void colourGroups(am3d_ctx* c, int ng, const int* gb1, const int* gb2, co
   }
   LAUNCH(c, k_color_sortkey, nblk(ng), BLK, ng, c->grpColor.p, gcount, layer, gb1, c->scene.p, partShift, c->nPart, nScenes, c->grpKey.p,
          c->grpVal.p);
-  cubRun(c, [&](void* t, size_t& b) {
-    return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit, c->stream);
-  });
+  sortPairs(c, c->grpKey.p, c->grpKeySorted.p, c->grpVal.p, c->grpOrder.p, ng, 0, endBit);
   // phases = runs of equal (layer, colour) in the sorted list
   c->phaseHead.ensure(ng + 2); c->phaseScan.ensure(ng + 2); c->sgPhase.ensure(ng + 2);
   LAUNCH(c, k_phase_heads, nblk(ng), BLK, ng, c->grpKeySorted.p, c->phaseHead.p);
@@ -210,9 +209,7 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
     if (bitsG + bitsB + bitsP > 64) throw AmError(AM3D_ECAPACITY, "hub run keys: groups x solver bodies x phases exceed 64 bits");
     LAUNCH(c, k_hub_entries, nblk(ng), BLK, ng, c->sgFlags.p, c->sgB1.p, c->sgB2.p, c->sgPhase.p, c->hubScan.p, bitsG, bitsB,
            c->hubKey.p, c->hubSlot.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, bitsG + bitsB + bitsP, c->stream);
-    });
+    sortPairs(c, c->hubKey.p, c->hubKeySorted.p, c->hubSlot.p, c->hubSlotSorted.p, ne, 0, bitsG + bitsB + bitsP);
     LAUNCH(c, k_hub_run_heads, nblk(ne), BLK, ne, c->hubKeySorted.p, bitsG, c->hubHead.p);
     int nr = scanTotal(c, c->hubHead, c->hubScan, ne);
     c->nHubRuns = nr;
@@ -398,9 +395,7 @@ static void rebuildMembers(am3d_ctx* c) {
   c->collCount.ensure(nc + 2); c->collStart.ensure(nc + 2);
   CK(cudaMemsetAsync(c->collCount.p, 0, (nc + 2) * sizeof(int), c->stream));
   LAUNCH(c, k_member_keys, nblk(nb), BLK, nb, nc, c->parent.p, c->memKey.p, c->memVal.p, c->collCount.p);
-  cubRun(c, [&](void* t, size_t& b) {
-    return cub::DeviceRadixSort::SortPairs(t, b, c->memKey.p, c->memKeySorted.p, c->memVal.p, c->members.p, nb, 0, bitsFor((unsigned long long)nc + 1), c->stream);
-  });
+  sortPairs(c, c->memKey.p, c->memKeySorted.p, c->memVal.p, c->members.p, nb, 0, bitsFor((unsigned long long)nc + 1));
   c->nMergedLeaves = scanTotal(c, c->collCount, c->collStart, nc);
 }
 static int countAlive(am3d_ctx* c) {
@@ -478,15 +473,11 @@ static void mergeStep(am3d_ctx* c) {
     LAUNCH(c, k_mseq_list, nblk(nbp), BLK, nbp, c->mflag.p, c->tmpI0.p, c->bp.key.p, c->msList.p, c->msLKey.p);
     if (c->bpTail) {  // pairs an unmerge handed back this step sit at the end of the table: restore ascending (lo, hi)
       c->msList2.ensure(nFlagged + 2); c->msLKey2.ensure(nFlagged + 2);
-      cubRun(c, [&](void* t, size_t& b) {
-        return cub::DeviceRadixSort::SortPairs(t, b, c->msLKey.p, c->msLKey2.p, c->msList.p, c->msList2.p, nFlagged, 0, 48, c->stream);
-      });
+      sortPairs(c, c->msLKey.p, c->msLKey2.p, c->msList.p, c->msList2.p, nFlagged, 0, 48);
       std::swap(c->msList, c->msList2);
     }
     LAUNCH(c, k_mseq_keys, nblk(nFlagged), BLK, nFlagged, c->msList.p, c->bp.b1.p, c->parent.p, c->uf.p, c->msKey.p, c->msVal.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->msKey.p, c->msKeySorted.p, c->msVal.p, c->msValSorted.p, nFlagged, 0, bitsFor((unsigned long long)ns), c->stream);
-    });
+    sortPairs(c, c->msKey.p, c->msKeySorted.p, c->msVal.p, c->msValSorted.p, nFlagged, 0, bitsFor((unsigned long long)ns));
     LAUNCH(c, k_seg_heads, nblk(nFlagged), BLK, nFlagged, c->msKeySorted.p, c->msHead.p);
     int nseg = scanTotal(c, c->msHead, c->msScan, nFlagged);
     LAUNCH(c, k_seg_fill, nblk(nFlagged), BLK, nFlagged, c->msHead.p, c->msScan.p, c->msSeg.p);
@@ -567,9 +558,7 @@ static bool unmergeStep(am3d_ctx* c, double dt) {
     // list position of the leaving pieces (Merging.java:269: bodies.addAll(additionQueue))
     c->grpKey.ensure(nb + 2); c->grpKeySorted.ensure(nb + 2); c->tmpI0.ensure(nb + 2); c->tmpI1.ensure(nb + 2);
     LAUNCH(c, k_unm_rank_keys, nblk(nb), BLK, nb, c->leavesFlag.p, c->parent.p, c->stamp.p, c->grpKey.p, c->tmpI0.p);
-    cubRun(c, [&](void* t, size_t& b) {
-      return cub::DeviceRadixSort::SortPairs(t, b, c->grpKey.p, c->grpKeySorted.p, c->tmpI0.p, c->tmpI1.p, nb, 0, 64, c->stream);
-    });
+    sortPairs(c, c->grpKey.p, c->grpKeySorted.p, c->tmpI0.p, c->tmpI1.p, nb, 0, 64);
     LAUNCH(c, k_unm_rank_scatter, nblk(nLeaving), BLK, nLeaving, c->tmpI1.p, c->leavesScan.p);
     LAUNCH(c, k_unm_apply, nblk(nb), BLK, nb, c->parent.p, c->collCuts.p, c->uf.p, c->leavesFlag.p, c->needNew.p, c->newScan.p, c->freeList.p,
            c->leavesScan.p, c->x.p, c->v.p, c->w.p, c->dv.p, c->stamp.p, c->nextStamp, c->collAlive.p, c->collMode.p, c->flags.p,

@@ -71,14 +71,6 @@ static int readInt(am3d_ctx* c, const int* p) {
   return v;
 }
 
-// exclusive scan of n ints (+ a trailing 0) so that out[n] is the total
-static int scanTotal(am3d_ctx* c, DevBuf<int>& in, DevBuf<int>& out, int n) {
-  out.ensure(n + 1);
-  CK(cudaMemsetAsync(in.p + n, 0, sizeof(int), c->stream));
-  cubRun(c, [&](void* t, size_t& b) { return cub::DeviceScan::ExclusiveSum(t, b, in.p, out.p, n + 1, c->stream); });
-  return readInt(c, out.p + n);
-}
-
 static int bitsFor(unsigned long long v) {
   int b = 1;
   while ((v >> b) && b < 63) b++;

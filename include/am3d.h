@@ -181,7 +181,8 @@ typedef struct am3d_params {
   /* Merging.java:30-54 */
   int32_t enable_merging;
   int32_t merge_pinned;
-  int32_t merge_cycle_condition;   /* unsupported (must be 0) */
+  int32_t merge_cycle_condition;   /* must be 0 (AM3D_EUNSUPPORTED): BodyPairContact.checkCyclesToUnmerge :375-394 recurses without end
+                                      over a static set once a cycle has been broken - nothing defined to reproduce */
   int32_t merge_stable_contact;
   int32_t merge_let_it_breathe;
   int32_t enable_unmerging;

@@ -35,7 +35,10 @@ def capture(fn, *a):
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return [], {}
@@ -125,7 +128,9 @@ def main():
                                    ("full_batch512", "512 x tower25platform (--scaling weak)", "batch", "bench_batch512.json"),
                                    ("full_stack", "1M-box stack, merging off", "stack", "bench_stack_m0.json"),
                                    ("full_funnel", "funnel + 4 000 torsos", "funnel", "bench_funnel20.json")):
-        rep = os.path.join(SRC, name + ".ncu-rep")
+        rep = os.path.join(SRC, name + "_raw.csv")   # raw page exported on the GPU box
+        if not os.path.exists(rep):
+            rep = os.path.join(SRC, name + ".ncu-rep")
         if not os.path.exists(rep):
             continue
         body = capture(ncu_summary.full, rep)

@@ -54,7 +54,10 @@ def launches(path):
 
 
 def full(path, pattern=None):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # `ncu -i report.ncu-rep --page raw --csv` done on the GPU box (the reports are too big to travel)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
