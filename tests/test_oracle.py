@@ -93,3 +93,34 @@ def test_config_d_dominos_cascade():
     ev = o.events()
     assert (ev[n0:, 1] == 0).sum() >= 300 and (ev[n0:, 1] == 1).sum() >= 300   # the cascade: unmerge / re-merge waves
     assert o.timings().n_bodies <= 6                                           # everything comes to rest merged again
+
+
+def test_magnet_pulls_while_active(oracle_lib):
+    """RigidBody.magnetic / activateMagnet (PGS.java:119,150,167): a box under a pinned magnetic slab hangs while the magnet
+    is active (the multipliers of its contacts are not clamped) and falls when it is switched off (LCPApp3D key 7)."""
+    from adaptivemerging_b200.ctypes_defs import default_params
+    from adaptivemerging_b200.scene import SceneBuilder
+    from oracle.oracle import Oracle
+    sb = SceneBuilder()
+    sb.add_plane((0, 0, 0), (0, 1, 0))
+    slab = sb.add_box((4, 1, 4), (0, 3.0, 0), pinned=True, name="magnet")
+    box = sb.add_box((1, 1, 1), (0.2, 2.01, -0.1), name="box")
+    sb.bodies[slab].magnetic = True
+    blob = sb.build()
+    p = default_params()
+    p.enable_merging = 0
+    o = Oracle(blob, p)
+    o.set_body_magnet(slab, 1)
+    o.set_body_magnet(box, 1)      # not magnetic: ignored
+    ys = []
+    for s in range(110):
+        if s == 60:
+            o.set_body_magnet(slab, 0)
+        o.step(0.05)
+        ys.append(float(o.bodies()["x"][box, 1]))
+    assert min(ys[:60]) > 1.9 and ys[-1] < 0.7
+    # without the magnet the box drops at once
+    o2 = Oracle(blob, p)
+    for s in range(30):
+        o2.step(0.05)
+    assert o2.bodies()["x"][box, 1] < 1.5

@@ -66,7 +66,7 @@ def main():
     out = ["# Bench lines, round 2 (B200, one fresh box per session; `tools/gpu_session_r2.sh`)\n",
            "Metric: body-steps/s. `resident` = state in HBM, CUDA events on the library stream; `e2e` = the same simulation steps",
            "with velocity pokes up from pinned host memory and the full body state down into pinned host memory, every step.",
-           "`roofline frac` = 752 B x contact-iterations / PGS sweep time / 6392.8 GB/s (SURVEY.md 8d); `traffic` = ncu DRAM bytes",
+           "`roofline frac` = 752 B x contact-iterations / PGS sweep time / the measured HBM peak of MEASURED_PEAKS.json (SURVEY.md 8d); `traffic` = ncu DRAM bytes",
            "per contact-iteration (r2_traffic.json) x the contact-iterations of a launch.\n"]
     for f in ("pytest_gpu.txt", "smoke.txt"):
         pth = os.path.join(SRC, f)
@@ -112,7 +112,9 @@ def main():
 
     for wl, title, flags in (("batch", "default bench workload (4096 x tower25platform)", " --no-also"),
                              ("batch512", "512 x tower25platform (--scaling weak)", " --scaling weak --no-also"),
-                             ("stack", "1M-box stack, merging off", " --workload stack --merging 0")):
+                             ("stack", "1M-box stack, merging off", " --workload stack --merging 0"),
+                             ("funnel_tree", "funnel + 4 000 torsos: the sphere-tree narrowphase kernels only (-k regex:\"k_narrow|k_tree\", 1 step)",
+                              " --workload funnel")):
         lcsv = os.path.join(SRC, f"launches_{wl}.csv")
         if not os.path.exists(lcsv):
             continue
@@ -173,10 +175,17 @@ def main():
             if not sel:
                 continue
             if key == "k_pgs_color<1>":
-                phases = bd.get("pgs_phases", len(sel))
-                sel = sel[:phases]
-                if len(sel) < phases:
-                    continue
+                # ONE iteration: the per-phase launches up to (and with) the launch that folds the trailing phases
+                # (k_pgs_tail<1>), or `pgs_phases` launches when there is none
+                seq = [r for r in rows if "k_pgs_color<1" in r[ix["Kernel Name"]] or "k_pgs_tail<1" in r[ix["Kernel Name"]]]
+                cut = next((i for i, r in enumerate(seq) if "k_pgs_tail<1" in r[ix["Kernel Name"]]), None)
+                if cut is not None:
+                    sel = seq[:cut + 1]
+                else:
+                    phases = bd.get("pgs_phases", len(sel))
+                    sel = sel[:phases]
+                    if len(sel) < phases:
+                        continue
                 iters = 1
             else:
                 sel = [max(sel, key=lambda r: fnum(r[ix["gpu__time_duration.sum"]]))]
