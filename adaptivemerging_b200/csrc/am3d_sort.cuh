@@ -174,8 +174,10 @@ static void amRadixSortPairs(am3d_ctx* c, const K* keysIn, K* keysOut, const V* 
   if (n <= 0) return;
   int passes = std::max(1, (endBit - beginBit + 7) / 8);
   int nTiles = (int)(((long long)n + RS_TILE - 1) / RS_TILE);
-  c->rsKeyTmp.ensure((size_t)n + 1);
-  c->rsValTmp.ensure((size_t)n + 1);
+  // (sized like the candidate-pair arrays, the largest thing sorted in a step, so that the temporaries do not grow step by step)
+  size_t want = std::max<size_t>((size_t)n + 1, c->pairKey.cap);
+  c->rsKeyTmp.ensure(want);
+  c->rsValTmp.ensure(want);
   c->rsHist.ensure((size_t)RS_RADIX * nTiles + 2);
   c->rsOff.ensure((size_t)RS_RADIX * nTiles + 2);
   K* kt = reinterpret_cast<K*>(c->rsKeyTmp.p);  // (64-bit slots: hold either key / value type)
