@@ -925,6 +925,7 @@ int am3d_set_option(am3d_ctx* c, const char* name, double value) {
   else if (!strcmp(name, "giant_warps")) c->useGiantWarps = (int)value;
   else if (!strcmp(name, "pgs_fast_rows")) c->fastRows = value != 0;
   else if (!strcmp(name, "tree_split")) c->treeSplit = value != 0;
+  else if (!strcmp(name, "scene_bfs")) c->useSceneBfs = value != 0;
   else if (!strcmp(name, "own_primitives")) c->ownPrimitives = value != 0;
   else if (!strcmp(name, "pgs_tail_fusion")) c->useTailFusion = value != 0;
   else if (!strcmp(name, "pgs_clusters")) c->useClusters = (int)value;

@@ -248,6 +248,8 @@ struct am3d_ctx {
   int ownPrimitives = 1;  // am3d_set_option("own_primitives", 0/1): hand-written radix sort / prefix sum (am3d_sort.cuh) or the CUB ones
   DevBuf<unsigned long long> rsKeyTmp, rsValTmp;
   DevBuf<int> rsHist, rsOff, scanSums;
+  int useSceneBfs = 1;    // am3d_set_option("scene_bfs", 0/1): breadth-first layers of the single sweep per scene (k_bfs_scenes) for batched contexts
+  DevBuf<int> sceneCnt, sceneStart, sceneCursor, sceneList;
   int useTailFusion = 1;  // am3d_set_option("pgs_tail_fusion", 0/1): trailing phases with one group per scene in one launch (k_pgs_tail)
   DevBuf<int> tailTable;
   int treeSplit = 1;      // am3d_set_option("tree_split", 0/1): tree x tree pairs with a large frontier are split into one task per node pair

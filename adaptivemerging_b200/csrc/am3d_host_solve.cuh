@@ -136,7 +136,18 @@ static void runSolve(am3d_ctx* c, double dt, bool sweep, bool post = false) {
       LAUNCH(c, k_bfs_seed_picked, nblk(ng), BLK, ng, gb1, gb2, gcount, c->picked.p, c->grpLayer.p);
       CK(cudaMemsetAsync(c->picked.p, 0, c->NB * sizeof(int), c->stream));  // b.picked = false (:371, :380)
     }
-    {
+    // batched scenes, up to the size from which a pass over all groups per layer is cheaper than bucketing them (measured:
+    // 512 scenes 10.97 -> 10.77 ms per step on average, 4096 scenes 49.58 -> 49.73): a CTA per scene, __syncthreads() between the layers
+    if (c->useSceneBfs && c->H.nscenes >= 32 && c->H.nscenes <= 64 * std::max(1, c->maxClusters)) {
+      int nsc = c->H.nscenes;
+      c->sceneCnt.ensure(nsc + 2); c->sceneStart.ensure(nsc + 2); c->sceneCursor.ensure(nsc + 2); c->sceneList.ensure(ng + 1);
+      CK(cudaMemsetAsync(c->sceneCnt.p, 0, (nsc + 1) * sizeof(int), c->stream));
+      CK(cudaMemsetAsync(c->sceneCursor.p, 0, (nsc + 1) * sizeof(int), c->stream));
+      LAUNCH(c, k_scene_count, nblk(ng), BLK, ng, gb1, c->scene.p, c->sceneCnt.p);
+      exclusiveSum(c, c->sceneCnt.p, c->sceneStart.p, nsc + 1);
+      LAUNCH(c, k_scene_fill, nblk(ng), BLK, ng, gb1, c->scene.p, c->sceneStart.p, c->sceneCursor.p, c->sceneList.p);
+      LAUNCH(c, k_bfs_scenes, nsc, 256, c->sceneStart.p, c->sceneList.p, gb1, gb2, gcount, c->grpLayer.p, c->bodyLevel.p, c->bfsRound.p);
+    } else {
       int ngv = ng;
       int *gl = c->grpLayer.p, *bl = c->bodyLevel.p, *rd = c->bfsRound.p;
       void* args[] = {&ngv, &gb1, &gb2, &gcount, &gl, &bl, &rd};

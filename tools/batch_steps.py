@@ -10,10 +10,16 @@ s = RigidBodySystem(0).load(blob, p)
 s.set_option("record_events", 0)
 for kv in sys.argv[3:]:
     s.set_option(kv.split("=")[0], float(kv.split("=")[1]))
+prof = int(os.environ.get("AM3D_PROFILE_STEP", "-1"))   # ncu --profile-from-start off: capture exactly this step
 for k in range(steps):
+    if k == prof:
+        import torch
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     s.advanceTime(0.05)
     w = (time.perf_counter() - t0) * 1e3
+    if k == prof:
+        torch.cuda.cudart().cudaProfilerStop()
     t = s.timings()
     if k >= 120:
         print(f"step {k:3d} wall {w:6.2f} contacts {t.n_contacts:8d} coll {t.n_collections:5d} detect {t.detection*1e3:5.2f} warm {t.warmstart*1e3:5.2f} "
