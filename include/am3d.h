@@ -370,9 +370,18 @@ int am3d_download_collection(am3d_ctx* ctx, int slot, double* out42);
 /* position of every leaf body's top-level entity (the body itself or its RigidCollection) in RigidBodySystem.bodies,
  * as a monotone key: sorting by it gives the list order the Java side has to mirror (Merging.java:105-110, :269-270) */
 int am3d_download_list_order(am3d_ctx* ctx, int64_t* out /* [n_bodies] */);
-/* engine options that are not reference parameters: "hub_min_degree" (body pairs per body from which a body is a
- * hub of the contact graph, 0 = never; default 64), "pgs_persistent" (0 never / 1 heuristic / 2 always),
- * "record_events" (merge / unmerge event log for am3d_download_events, default 1; 0 saves a read-back per merge step) */
+/* engine options that are not reference parameters (none of them changes a result except hub_min_degree):
+ *   "hub_min_degree"   body pairs per body from which a body is a hub of the contact graph, 0 = never; default 64
+ *   "record_events"    merge / unmerge event log for am3d_download_events, default 1; 0 saves a read-back per merge step
+ *   "pgs_persistent"   0 never / 1 heuristic / 2 always: the whole solve in one cooperative launch
+ *   "pgs_clusters"     0/1: batched scenes partitioned over thread-block clusters (74 - 2 300 scenes)
+ *   "pgs_tail_fusion"  0/1: trailing phases that hold one group per scene folded into one launch
+ *   "pgs_fast_rows"    0/1: branch-free PGS row update (0 = the plain form everywhere)
+ *   "giant_warps", "giant_chunk"   sphere-tree pairs with >= 65 contacts solved by a warp; contacts per chunk (512)
+ *   "tree_split"       0/1: tree x tree pairs with a large frontier split into one narrowphase task per node pair
+ *   "scene_bfs"        0/1: breadth-first layers of the single sweep per scene for batched contexts
+ *   "own_primitives"   0/1: hand-written radix sort / prefix sum (1) or the CUB ones (0, the cross-check)
+ *   "merge_exact_max_pairs"   mergeable pairs per component up to which Merging.merge is replayed in sequence (16 384) */
 int am3d_set_option(am3d_ctx* ctx, const char* name, double value);
 int am3d_mark(am3d_ctx* ctx, int slot);
 int am3d_elapsed_ms(am3d_ctx* ctx, double* ms);
