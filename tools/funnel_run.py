@@ -1,5 +1,6 @@
 """Config F (funnel + n x 10 x n torso_flux sphere-tree bodies) for a number of steps: per-step timings into a JSON-lines
-file.  Usage (GPU box): python tools/funnel_run.py n steps y0 out.jsonl"""
+file.  Usage (GPU box): python tools/funnel_run.py n steps y0 out.jsonl [max_contacts]
+(max_contacts: stop once a step holds more contacts than this - the full-size pile outgrows one GPU's memory while it lands)"""
 import json
 import os
 import sys
@@ -12,6 +13,7 @@ from bench import build_workload  # noqa: E402
 from adaptivemerging_b200.system import RigidBodySystem  # noqa: E402
 
 n, steps, y0, out = int(sys.argv[1]), int(sys.argv[2]), float(sys.argv[3]), sys.argv[4]
+max_contacts = float(sys.argv[5]) if len(sys.argv) > 5 else float("inf")
 t0 = time.time()
 blob, p, desc = build_workload("funnel", n, 1, y0)
 nb = int((blob.a["body_type"] != 1).sum())
@@ -35,5 +37,9 @@ with open(out, "w") as f:
         f.flush()
         if (k + 1) % 10 == 0:
             print(row, flush=True)
+        if t.n_contacts > max_contacts:
+            print(f"stopping after step {k + 1}: {t.n_contacts} contacts > {max_contacts:.3g}", flush=True)
+            print(row, flush=True)
+            break
 b = s.bodies()
 print("finite:", bool(np.isfinite(b["x"]).all()), "y range", float(b["x"][:, 1].min()), float(b["x"][:, 1].max()), "total wall", time.time() - wall0)
